@@ -1,0 +1,146 @@
+/* vasr.h — C ABI of libvasr.so, the B200 (sm_100a) inference path for VELOCITY-ASR v2.
+ *
+ * The reference (shaderko/velocity-asr) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b).  Its two seams are the package API (velocity_asr/__init__.py:95-145)
+ * and the scan_mode switch (velocity_asr/ssm.py:119-126).  Each entry point below replaces
+ * one reference callable; the Python package in velocity-asr_b200/velocity_asr binds them
+ * with ctypes and keeps the reference's names and argument meaning.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  `*_dev` pointers are device memory on
+ *     the handle's GPU, `*_host` pointers are host memory.  All tensors are contiguous fp32
+ *     in the reference's own layouts (channels-last: (B, T, C)).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     asynchronous with respect to the host unless the name ends in `_host`.
+ *   - every function returns VASR_OK or an error code; vasr_last_error() gives the text for
+ *     the calling thread.  There is no CPU fallback: without a CUDA device every compute
+ *     entry point fails with VASR_ERR_CUDA.
+ *   - the caller owns all buffers it passes; the handle owns weights and workspace.  The
+ *     workspace grows on first use of a larger (B, S) and is then reused: no allocation on
+ *     the hot path after warm-up.  One handle per GPU per process; calls on one handle must
+ *     not overlap.
+ */
+#ifndef VASR_H_
+#define VASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vasr_handle vasr_handle;
+
+enum {
+  VASR_OK = 0,
+  VASR_ERR_INVALID = 1,     /* bad argument / unknown name -> ValueError (ssm.py:126)            */
+  VASR_ERR_SHAPE = 2,       /* shape the model cannot take -> RuntimeError (model.py:125)        */
+  VASR_ERR_CUDA = 3,        /* CUDA runtime / no device                                          */
+  VASR_ERR_STATE = 4,       /* weights missing or not committed                                  */
+  VASR_ERR_UNSUPPORTED = 5  /* configuration outside what the kernels are built for              */
+};
+
+enum { VASR_SCAN_SEQUENTIAL = 0, VASR_SCAN_PARALLEL = 1, VASR_SCAN_MAMBA = 2 };
+
+/* Mirrors VelocityASRConfig (velocity_asr/model.py:23-68); dropout / checkpointing /
+ * use_compile have no meaning for inference and are not carried. */
+typedef struct vasr_config {
+  int32_t mel_bins;              /* 80  */
+  int32_t d_model;               /* 192 */
+  int32_t ssm_layers;            /* 8   */
+  int32_t ssm_state_dim;         /* 64  */
+  int32_t ssm_expand_ratio;      /* 2   */
+  int32_t ssm_kernel_size;       /* 4   */
+  int32_t global_ssm_layers;     /* 2   */
+  int32_t global_ssm_state_dim;  /* 32  */
+  int32_t attention_heads;       /* 4   */
+  int32_t attention_dim;         /* 48  */
+  int32_t vocab_size;            /* 1000 */
+  int32_t scan_mode;             /* VASR_SCAN_*; the reference default is PARALLEL (model.py:60) */
+} vasr_config;
+
+const char* vasr_last_error(void);
+const char* vasr_version(void);
+
+/* ---- handle and weights: VELOCITYASR.__init__ / load_state_dict (model.py:255-299, 416-431) */
+int vasr_create(const vasr_config* cfg, int device, vasr_handle** out);
+void vasr_destroy(vasr_handle* h);
+/* One tensor of the reference state_dict, by its reference key (the 208 names of SURVEY.md
+ * section 8b), fp32, host memory, numel elements.  Two extra optional keys override the
+ * built-in front-end tables: "frontend.mel_filterbank" (n_mels x 201) and "frontend.window"
+ * (400).  Unknown keys -> VASR_ERR_INVALID. */
+int vasr_set_weight(vasr_handle* h, const char* name, const float* host, int64_t numel);
+/* Packs the tensors into kernel layouts; fails with VASR_ERR_STATE naming the first missing key. */
+int vasr_commit_weights(vasr_handle* h);
+
+/* ---- shape helpers: audio.py:104-112 (center=False after reflect pad), model.py:370-383 */
+int64_t vasr_num_frames(int64_t samples);   /* 1 + samples / 160                 */
+int64_t vasr_num_tokens(int64_t frames);    /* (frames + 1) / 2                  */
+
+/* ---- compute_mel_spectrogram (velocity_asr/audio.py:65-143)
+ * pcm (B, S) -> mel (B, T, n_mels), T = vasr_num_frames(S).  S must be > 200 (reflect pad). */
+int vasr_log_mel(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int normalize,
+                 float* mel_dev, void* stream);
+
+/* ---- VELOCITYASR.forward (velocity_asr/model.py:333-368)
+ * mel (B, T, mel_bins) -> logits (B, L, vocab), L = vasr_num_tokens(T).  The three feature
+ * pointers are the return_features dict ('temporal_binding', 'local_features',
+ * 'fused_features'), each (B, L, d_model); pass NULL to skip. */
+int vasr_forward(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, float* logits_dev,
+                 float* feat_tb_dev, float* feat_local_dev, float* feat_fused_dev, void* stream);
+
+/* ---- module-level seams used by the parity tests (reference classes in __all__) ---------- */
+/* SSMBlock.forward (ssm.py:404-427).  stack 0 = local_ssm.layers[layer], 1 =
+ * global_context.global_ssm.layers[layer]; scan_mode < 0 = the mode the reference would use
+ * (config scan_mode for local, PARALLEL for global, ssm.py:529-538). */
+int vasr_ssm_block(vasr_handle* h, int stack, int layer, int scan_mode, const float* x_dev,
+                   int64_t B, int64_t L, float* out_dev, void* stream);
+/* HierarchicalGlobalContext.forward (attention.py:283-319): (B, L, d_model) -> same. */
+int vasr_global_context(vasr_handle* h, const float* local_dev, int64_t B, int64_t L,
+                        float* out_dev, void* stream);
+/* CTCOutputHead.forward (model.py:229-239): (B, L, d_model) -> (B, L, vocab). */
+int vasr_ctc_head(vasr_handle* h, const float* x_dev, int64_t B, int64_t L, float* logits_dev,
+                  void* stream);
+
+/* ---- the scan operator: SelectiveSSM._sequential_scan / _parallel_scan / _mamba_scan
+ * (ssm.py:134-337).  x, dt: (B, L, Di) with row strides ldx, lddt; Bm, Cm: (B, L, N) with row
+ * strides ldb, ldc; A: (N), D: (Di) or NULL (no skip term); z: (B, L, Di) stride ldz or NULL
+ * (when given, y is multiplied by silu(z), ssm.py:129); y: (B, L, Di) stride ldy.
+ * N in {32, 64}.  All device pointers.  No handle: the operator is stateless. */
+int vasr_selective_scan(const float* x, int64_t ldx, const float* dt, int64_t lddt, const float* A,
+                        const float* Bm, int64_t ldb, const float* Cm, int64_t ldc, const float* D,
+                        const float* z, int64_t ldz, float* y, int64_t ldy, int64_t B, int64_t L,
+                        int64_t Di, int64_t N, int scan_mode, void* stream);
+
+/* ---- ctc_greedy_decode (velocity_asr/decode.py:27-71)
+ * logits (B, L, V) -> tokens (B, L) int32 left-packed, lens (B) int32.  argmax ties -> lowest
+ * index; blanks dropped; repeats collapsed when collapse != 0; a blank resets the repeat state. */
+int vasr_ctc_greedy(const float* logits_dev, int64_t B, int64_t L, int64_t V, int blank, int collapse,
+                    int32_t* tokens_dev, int32_t* lens_dev, void* stream);
+
+/* ---- transcribe: load -> mel -> model -> greedy (scripts/transcribe.py:69-82), batched.
+ * tokens (B, L) int32, lens (B); L = vasr_num_tokens(vasr_num_frames(S)). */
+int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S,
+                    int32_t* tokens_dev, int32_t* lens_dev, void* stream);
+/* Host buffers in, host buffers out; H2D and D2H copies inside; synchronous. */
+int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64_t S,
+                         int32_t* tokens_host, int32_t* lens_host);
+
+/* ---- a plain linear layer (F.linear), exposed so the GEMM kernel can be tested alone.
+ * act: 0 none, 1 gelu(erf), 2 softplus, 3 sigmoid.  x (M, K) stride ldx, w (N, K), bias (N) or
+ * NULL, out (M, N) stride ldo.  K % 16 == 0. */
+int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev,
+                float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream);
+
+/* ---- bookkeeping for the bench: kernels launched by this handle since creation, and the
+ * share of the last vasr_transcribe spent in the scan (device ms, CUDA events on `stream`)
+ * when timing is enabled with vasr_set_timing(h, 1). */
+int64_t vasr_kernel_launches(const vasr_handle* h);
+int vasr_set_timing(vasr_handle* h, int enabled);
+int vasr_last_timing(const vasr_handle* h, float* scan_ms, int32_t* scan_launches, float* total_ms);
+int64_t vasr_workspace_bytes(const vasr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VASR_H_ */

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI of libvasr.so) with the reference.
+
+Checked against (1) golden fixtures produced by running the reference (tests/golden), (2) the
+numpy oracle on fresh seeded inputs, (3) size-independent properties at BASELINE sizes.
+Tolerances (BASELINE.json north_star): mel 1e-4 absolute; activations / logits 1e-3 relative
+to the tensor's max magnitude (fp32 path: observed ~1e-5); token ids bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import fixtures_util as FU
+import velocity_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 1e-3
+MEL_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def va():
+    import velocity_asr
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return velocity_asr
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a.astype(np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def make_model(va, mode, amp=False):
+    torch.manual_seed(FU.WEIGHT_SEED)
+    m = va.VELOCITYASR(va.VelocityASRConfig(scan_mode=mode))
+    if amp:
+        m.load_state_dict(FU.amplify_state_dict(m.state_dict()))
+    return m.cuda().eval()
+
+
+def np_sd(m):
+    return {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+
+
+# ------------------------------------------------------------------ projections ----------
+@pytest.mark.parametrize("M,K,N,act", [(1, 16, 1, None), (130, 192, 768, None), (257, 384, 512, "softplus"),
+                                       (100, 192, 1000, None), (300, 48, 192, None), (64, 240, 192, "gelu"),
+                                       (513, 400, 402, None), (77, 384, 48, "sigmoid")])
+def test_linear(va, M, K, N, act):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    y = va.linear(x.cuda(), w.cuda(), b.cuda(), activation=act)
+    ref = O.linear(x.double().numpy(), w.double().numpy(), b.double().numpy())
+    ref = {None: lambda v: v, "gelu": O.gelu, "softplus": O.softplus, "sigmoid": O.sigmoid}[act](ref)
+    assert y.shape == (M, N)
+    assert rel(y, ref) < 2e-6
+    y2 = va.linear(x.cuda(), w.cuda())          # no bias
+    assert rel(y2, O.linear(x.double().numpy(), w.double().numpy())) < 2e-6
+
+
+# ------------------------------------------------------------------ front end ------------
+def test_log_mel_golden(va, golden):
+    g = golden("frontend")
+    audio = FU.synth_audio(2, 16000).cuda()
+    mel = va.compute_mel_spectrogram(audio)
+    assert mel.shape == (2, 101, 80)
+    assert np.abs(mel.cpu().numpy() - g["mel"]).max() < MEL_ATOL
+    raw = va.compute_mel_spectrogram(audio, normalize=False)
+    assert np.abs(raw.cpu().numpy() - g["mel_raw"]).max() < MEL_ATOL
+    odd = va.compute_mel_spectrogram(FU.synth_audio(3, 4037, seed=99).cuda())
+    assert odd.shape == (3, 26, 80)
+    assert np.abs(odd.cpu().numpy() - g["mel_odd"]).max() < MEL_ATOL
+    one = va.compute_mel_spectrogram(audio[0, :800])
+    assert one.shape == (6, 80)
+    assert np.abs(one.cpu().numpy() - g["mel_1d"]).max() < MEL_ATOL
+
+
+def test_log_mel_oracle_15s(va, golden):
+    g = golden("frontend")
+    audio = FU.synth_audio(3, 240000, seed=5)
+    mel = va.compute_mel_spectrogram(audio.cuda())
+    assert mel.shape == (3, 1501, 80)
+    ref = O.log_mel(audio.numpy(), filters=g["filterbank"], window=g["window"])
+    assert np.abs(mel.cpu().numpy() - ref).max() < MEL_ATOL
+    # per (utterance, bin): zero mean, unit unbiased std over time (audio.py:132-135)
+    assert mel.mean(1).abs().max() < 1e-4
+    assert (mel.std(1) - 1).abs().max() < 1e-4
+
+
+def test_log_mel_rejects_short_and_cpu(va):
+    with pytest.raises(RuntimeError):
+        va.compute_mel_spectrogram(torch.zeros(1, 150).cuda())     # reflect pad needs > 200 samples
+    with pytest.raises(RuntimeError):
+        va.compute_mel_spectrogram(torch.zeros(1, 16000))          # no CPU path
+
+
+# ------------------------------------------------------------------ selective scan -------
+def test_scan_golden(va, golden):
+    g = golden("scan_ops")
+    for case in g["cases"]:
+        name, b, L, di, n, seed, st = eval(case)
+        x, dt, A, Bm, Cm, D = [torch.from_numpy(a).cuda() for a in FU.scan_inputs(b, L, di, n, seed, st)]
+        ys = va.selective_scan(x, dt, A, Bm, Cm, D, scan_mode="sequential")
+        yp = va.selective_scan(x, dt, A, Bm, Cm, D, scan_mode="parallel")
+        assert rel(ys, g[name + "_seq"]) < 1e-4, name
+        assert rel(yp, g[name + "_par"]) < 1e-4, name
+        ym = va.selective_scan(x, dt, A, Bm, Cm, D, scan_mode="mamba")
+        assert torch.equal(ym, ys)
+
+
+@pytest.mark.parametrize("n,structured", [(64, True), (64, False), (32, True), (32, False), (16, True)])
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_scan_oracle(va, n, structured, mode):
+    L = 203 if mode == "sequential" else 71            # not a multiple of the 32-step chunk / of 8
+    x, dt, A, Bm, Cm, D = FU.scan_inputs(2, L, 128, n, 100 + n, structured)
+    rs = np.random.RandomState(3)
+    z = rs.standard_normal(x.shape).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    y = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode=mode)
+    d = lambda a: a.astype(np.float64)
+    ref = O.selective_scan(d(x), d(dt), d(A), d(Bm), d(Cm), d(D), mode) * O.silu(d(z))
+    assert rel(y, ref) < 1e-4
+    y0 = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), None, scan_mode=mode)   # no skip, no gate
+    assert rel(y0, O.selective_scan(d(x), d(dt), d(A), d(Bm), d(Cm), None, mode)) < 1e-4
+
+
+def test_scan_mamba_signature(va):
+    x, dt, A, Bm, Cm, D = FU.scan_inputs(2, 50, 384, 64, 77, True)
+    t = lambda a: torch.from_numpy(a).cuda()
+    y = va.selective_scan_fn(t(x).transpose(1, 2).contiguous(), t(dt).transpose(1, 2).contiguous(),
+                             t(A).unsqueeze(0).expand(384, -1).contiguous(), t(Bm).unsqueeze(1), t(Cm).unsqueeze(1),
+                             t(D))
+    assert y.shape == (2, 384, 50)
+    d = lambda a: a.astype(np.float64)
+    assert rel(y.transpose(1, 2), O.scan_sequential(d(x), d(dt), d(A), d(Bm), d(Cm), d(D))) < 1e-4
+
+
+def test_scan_properties_config2_size(va):
+    """BASELINE config 2 shape (64 x 751 x 384, N = 64): causality, linearity in x, batch independence."""
+    B, L, Di, N = 64, 751, 384, 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, L, Di, device="cuda", generator=g)
+    dt = torch.nn.functional.softplus(torch.randn(B, L, Di, device="cuda", generator=g))
+    Bm = torch.randn(B, L, N, device="cuda", generator=g)
+    Cm = torch.randn(B, L, N, device="cuda", generator=g)
+    A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32)
+    D = torch.randn(Di, device="cuda", generator=g)
+    y = va.selective_scan(x, dt, A, Bm, Cm, D)
+    assert torch.isfinite(y).all()
+    assert torch.equal(y, va.selective_scan(x, dt, A, Bm, Cm, D))                      # deterministic
+    y_pre = va.selective_scan(x[:, :300].contiguous(), dt[:, :300].contiguous(), A, Bm[:, :300].contiguous(),
+                              Cm[:, :300].contiguous(), D)
+    assert torch.equal(y_pre, y[:, :300])                                               # causal
+    y2 = va.selective_scan(2 * x, dt, A, Bm, Cm, D)
+    assert (y2 - 2 * y).abs().max() <= 1e-5 * y.abs().max()                             # linear in x
+    y_one = va.selective_scan(x[5:6].contiguous(), dt[5:6].contiguous(), A, Bm[5:6].contiguous(),
+                              Cm[5:6].contiguous(), D)
+    assert torch.equal(y_one[0], y[5])                                                  # shards independently
+    sub = slice(0, 2)
+    d = lambda a: a[sub].double().cpu().numpy()
+    ref = O.scan_sequential(d(x), d(dt), A.double().cpu().numpy(), d(Bm), d(Cm), D.double().cpu().numpy())
+    assert rel(y[sub], ref) < 1e-4
+
+
+# ------------------------------------------------------------------ blocks ---------------
+def test_blocks_golden(va, golden):
+    g = golden("blocks")
+    rs = np.random.RandomState(21)
+    xin = torch.from_numpy(rs.standard_normal((2, 75, 192)).astype(np.float32)).cuda()
+    xlong = torch.from_numpy(rs.standard_normal((1, 1100, 192)).astype(np.float32)).cuda()
+    m = make_model(va, "sequential", amp=True)
+    assert rel(m.run_ssm_block(xin, 0, "local"), g["local_block0_seq"]) < LOGIT_RTOL
+    assert rel(m.run_ssm_block(xin, 0, "local", scan_mode="parallel"), g["local_block0_par"]) < LOGIT_RTOL
+    assert rel(m.run_global_context(xin), g["global_context"]) < LOGIT_RTOL
+    assert rel(m.run_global_context(xlong)[:, ::11], g["global_context_L1100"]) < LOGIT_RTOL
+    assert rel(m.run_ctc_head(xin)[:, ::5], g["ctc_head"]) < LOGIT_RTOL
+    sd = np_sd(m)
+    x64 = xin.double().cpu().numpy()
+    assert rel(m.run_ssm_block(xin, 3, "local"), O.ssm_block(x64, sd, "local_ssm.layers.3.", "sequential")) < 1e-4
+    assert rel(m.run_ssm_block(xin, 1, "global"),
+               O.ssm_block(x64, sd, "global_context.global_ssm.layers.1.", "parallel")) < 1e-4
+
+
+# ------------------------------------------------------------------ whole model ----------
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+@pytest.mark.parametrize("amp", [False, True])
+def test_forward_golden(va, golden, mode, amp):
+    g = golden("model_small")
+    mel = torch.from_numpy(golden("frontend")["mel"]).cuda()
+    m = make_model(va, mode, amp)
+    logits, f = m(mel, return_features=True)
+    tag = f"{mode}{'_amp' if amp else ''}"
+    assert logits.shape == (2, 51, 1000)
+    assert rel(f["temporal_binding"], g[tag + "_tb"]) < LOGIT_RTOL
+    assert rel(f["local_features"], g[tag + "_local"]) < LOGIT_RTOL
+    assert rel(f["fused_features"], g[tag + "_fused"]) < LOGIT_RTOL
+    assert rel(logits, g[tag + "_logits"]) < LOGIT_RTOL
+    toks = va.ctc_greedy_decode(logits)
+    assert toks == [[int(t) for t in row if t >= 0] for row in g[tag + "_tokens"]]
+    assert torch.equal(m(mel), logits)          # plain call, and run-to-run reproducible
+
+
+def test_mamba_mode_equals_sequential(va, golden):
+    mel = torch.from_numpy(golden("frontend")["mel"]).cuda()
+    a = make_model(va, "sequential", True)(mel)
+    b = make_model(va, "mamba", True)(mel)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_config1_end_to_end(va, golden, mode):
+    """BASELINE config 1: 1 x 10 s, mel + forward + greedy."""
+    g = golden("config1")
+    audio = FU.synth_audio(1, 160000).cuda()
+    m = make_model(va, mode)
+    mel = va.compute_mel_spectrogram(audio)
+    assert np.abs(mel[:, ::50].cpu().numpy() - g["mel_sub"]).max() < MEL_ATOL
+    logits = m(mel)
+    assert logits.shape == (1, 501, 1000)
+    assert rel(logits[:, ::25], g[mode + "_logits_sub"]) < LOGIT_RTOL
+    am = logits.argmax(-1).cpu().numpy()
+    safe = g[mode + "_margin"] > 1e-3            # frames whose argmax is not a near-tie in the reference
+    assert (am == g[mode + "_argmax"])[safe].all()
+    assert (am == g[mode + "_argmax"]).mean() >= 0.99
+    assert va.ctc_greedy_decode(logits)[0] == m.transcribe(audio)[0]
+    if (am == g[mode + "_argmax"]).all():
+        assert m.transcribe(audio)[0] == g[mode + "_tokens"].tolist()
+
+
+def test_transcribe_paths_agree_and_shard(va):
+    """Fused PCM->tokens == mel + forward + greedy; host-buffer entry == device entry; an
+    utterance decodes the same alone as inside a batch (the data-parallel sharding rule)."""
+    m = make_model(va, "sequential", amp=True)
+    audio = FU.synth_audio(6, 48000, seed=11)
+    dev = m.transcribe(audio.cuda())
+    host = m.transcribe(audio.pin_memory())
+    sep = va.ctc_greedy_decode(m(va.compute_mel_spectrogram(audio.cuda())))
+    assert dev == host == sep
+    assert m.transcribe(audio[3:5].cuda()) == dev[3:5]
+    assert m.transcribe(audio[2].cuda()) == dev[2:3]
+    oracle = O.transcribe(audio[:2].numpy(), np_sd(m), dict(scan_mode="sequential"))
+    assert oracle == dev[:2]
+
+
+def test_long_form_needs_longer_table(va):
+    m = make_model(va, "sequential")
+    mel = torch.randn(1, 10003, 80, device="cuda")      # 5002 tokens > pe_time rows (model.py:87,125)
+    with pytest.raises(RuntimeError):
+        m(mel)
+    m.extend_positional_table(6000)
+    out = m(mel)
+    assert out.shape == (1, 5002, 1000) and torch.isfinite(out).all()
+    sd = np_sd(m)
+    ref_tb = O.temporal_binding(mel[:, :400].double().cpu().numpy(), sd)
+    _, f = m(mel[:, :400].contiguous(), return_features=True)
+    assert rel(f["temporal_binding"], ref_tb) < 1e-4
+
+
+# ------------------------------------------------------------------ CTC greedy -----------
+def test_ctc_greedy_known_answers(va, golden):
+    g = golden("decode")
+    for i in range(5):
+        lg = torch.nn.functional.one_hot(torch.from_numpy(g[f"in{i}"]).long()[None], 10).float().cuda()
+        assert va.ctc_greedy_decode(lg)[0] == g[f"out{i}"].tolist()
+        assert va.ctc_greedy_decode(lg, collapse_repeated=False)[0] == g[f"out_nocollapse{i}"].tolist()
+    tie = torch.zeros(1, 3, 6); tie[0, 0, 2] = tie[0, 0, 4] = 1.0; tie[0, 1, 5] = 1.0
+    assert va.ctc_greedy_decode(tie.cuda())[0] == g["tie_out"].tolist()
+    assert va.ctc_greedy_decode(torch.zeros(2, 0, 5).cuda()) == [[], []]
+    assert va.ctc_greedy_decode(torch.zeros(0, 4, 5).cuda()) == []
+    dec = va.CTCDecoder(va.create_default_vocabulary(10))
+    lg = torch.nn.functional.one_hot(torch.tensor([[4, 4, 0, 5, 3, 6]]), 10).float().cuda()
+    assert dec.decode_greedy(lg) == ["ab c"]
+
+
+def test_ctc_greedy_random_vs_oracle(va):
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randint(0, 4, (7, 1003), generator=g)           # many blanks and repeats, ragged outputs
+    lg = torch.nn.functional.one_hot(pred, 1000).float() + 0.01 * torch.rand(7, 1003, 1000, generator=g)
+    got = va.ctc_greedy_decode(lg.cuda())
+    assert got == O.ctc_greedy_decode(lg.numpy())
+    assert va.ctc_greedy_decode(lg.cuda(), blank_token=2) == O.ctc_greedy_decode(lg.numpy(), blank_token=2)
+
+
+# ------------------------------------------------------------------ errors ---------------
+def test_error_behaviour(va):
+    with pytest.raises(ValueError):
+        va.VELOCITYASR(va.VelocityASRConfig(scan_mode="bogus"))               # ssm.py:126
+    with pytest.raises(ValueError):
+        va.selective_scan(*[torch.zeros(1, 1, 64).cuda()] * 2, torch.zeros(64).cuda(),
+                          *[torch.zeros(1, 1, 64).cuda()] * 2, scan_mode="bogus")
+    with pytest.raises(NotImplementedError):
+        va.VELOCITYASR.from_pretrained("velocity-asr-v2-base")                # model.py:409-413
+    m = va.VELOCITYASR()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 10, 80))                                             # CPU: no fallback
+    m = m.cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 10, 81).cuda())

@@ -1,0 +1,58 @@
+"""Live comparison of the oracle with the unmodified reference, when it is importable
+(/root/reference in the build container, or baseline/_ref).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import fixtures_util as FU
+import velocity_oracle as O
+from refload import load_reference
+
+R = load_reference()
+pytestmark = pytest.mark.skipif(R is None, reason="reference tree not present on this box")
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_mel_and_forward_fresh_seed():
+    audio = FU.synth_audio(2, 24000, seed=321)
+    with torch.no_grad():
+        mel = R.compute_mel_spectrogram(audio)
+    assert np.abs(O.log_mel(audio.numpy()) - mel.numpy()).max() < 1e-4
+    for mode in ("sequential", "parallel"):
+        torch.manual_seed(5)
+        m = R.VELOCITYASR(R.VelocityASRConfig(scan_mode=mode)).eval()
+        m.load_state_dict(FU.amplify_state_dict(m.state_dict(), seed=9))
+        sd = {k: v.numpy() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            ref = m(mel)
+        got = O.forward(mel.numpy(), sd, dict(scan_mode=mode))
+        assert rel(got, ref.numpy()) < 5e-5
+        assert O.ctc_greedy_decode(got) == R.ctc_greedy_decode(ref)
+
+
+def test_product_parameter_tree_draws_reference_weights():
+    import velocity_asr
+    torch.manual_seed(11)
+    a = R.VELOCITYASR(R.VelocityASRConfig()).state_dict()
+    torch.manual_seed(11)
+    b = velocity_asr.VELOCITYASR(velocity_asr.VelocityASRConfig()).state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_yaml_mapping_matches_reference_defaults():
+    import os
+    import velocity_asr
+    path = "/root/reference/configs/model.yaml"
+    if not os.path.exists(path):
+        pytest.skip("configs/model.yaml only exists in the source tree")
+    c = velocity_asr.config_from_yaml(path)
+    r = R.VelocityASRConfig()
+    for f in ("mel_bins", "d_model", "ssm_layers", "ssm_state_dim", "ssm_expand_ratio", "ssm_kernel_size",
+              "global_ssm_layers", "global_ssm_state_dim", "attention_heads", "attention_dim", "vocab_size",
+              "scan_mode", "dropout"):
+        assert getattr(c, f) == getattr(r, f), f

@@ -1,0 +1,121 @@
+// context.cu — streaming kernels of the hierarchical global context
+// (velocity_asr/attention.py): adaptive average pooling (:63-78), the softmax(QK^T/sqrt(hd))V
+// core of the 4-head cross-attention over K2 <= 64 pooled keys (:143-161), and the gated mix
+// g*local_t + (1-g)*global_t (:208-215).  The projections around them run through gemm.cu.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vasr {
+
+namespace {
+
+// F.adaptive_avg_pool1d: window i = [floor(i L / K), ceil((i+1) L / K))
+__global__ void __launch_bounds__(256) adaptive_pool_kernel(const float* __restrict__ x, int64_t ldx,
+                                                            float* __restrict__ out, int64_t L, int64_t K,
+                                                            int C) {
+  const int64_t i = blockIdx.x, b = blockIdx.y;
+  const int64_t s = (i * L) / K;
+  const int64_t e = ((i + 1) * L + K - 1) / K;
+  const float inv = 1.0f / (float)(e - s);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float acc = 0.f;
+    for (int64_t t = s; t < e; ++t) acc += x[(b * L + t) * ldx + c];
+    out[(b * K + i) * C + c] = acc * inv;
+  }
+}
+
+// One thread per (token, head).  K/V rows of the utterance sit in shared memory; the K2 <= 64
+// scores are recomputed in the second pass instead of being kept (hd = 12 -> 12 FMAs each).
+constexpr int ATT_TOK = 64;
+constexpr int ATT_MAX_HD = 16;
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int64_t ldq,
+                                                        const float* __restrict__ kv, float* __restrict__ o,
+                                                        int64_t ldo, int64_t L, int64_t Kk, int heads, int hd) {
+  extern __shared__ float skv[];  // Kk x (2*A)
+  const int A = heads * hd;
+  const int64_t b = blockIdx.y;
+  for (int idx = threadIdx.x; idx < Kk * 2 * A; idx += blockDim.x) skv[idx] = kv[b * Kk * 2 * A + idx];
+  __syncthreads();
+  const int tok = threadIdx.x / heads, hh = threadIdx.x % heads;
+  const int64_t t = (int64_t)blockIdx.x * ATT_TOK + tok;
+  if (tok >= ATT_TOK || t >= L) return;
+  const float scale = 1.0f / sqrtf((float)hd);
+  float qv[ATT_MAX_HD];
+  const float* qr = q + (b * L + t) * ldq + hh * hd;
+#pragma unroll
+  for (int d = 0; d < ATT_MAX_HD; ++d) qv[d] = d < hd ? qr[d] : 0.f;
+  float mx = -INFINITY;
+  for (int64_t kx = 0; kx < Kk; ++kx) {
+    const float* kr = skv + kx * 2 * A + hh * hd;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < ATT_MAX_HD; ++d)
+      if (d < hd) s = fmaf(qv[d], kr[d], s);
+    mx = fmaxf(mx, s * scale);
+  }
+  float den = 0.f, acc[ATT_MAX_HD];
+#pragma unroll
+  for (int d = 0; d < ATT_MAX_HD; ++d) acc[d] = 0.f;
+  for (int64_t kx = 0; kx < Kk; ++kx) {
+    const float* kr = skv + kx * 2 * A + hh * hd;
+    const float* vr = kr + A;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < ATT_MAX_HD; ++d)
+      if (d < hd) s = fmaf(qv[d], kr[d], s);
+    const float p = expf(s * scale - mx);
+    den += p;
+#pragma unroll
+    for (int d = 0; d < ATT_MAX_HD; ++d)
+      if (d < hd) acc[d] = fmaf(p, vr[d], acc[d]);
+  }
+  const float inv = 1.0f / den;
+  float* orow = o + (b * L + t) * ldo + hh * hd;
+#pragma unroll
+  for (int d = 0; d < ATT_MAX_HD; ++d)
+    if (d < hd) orow[d] = acc[d] * inv;
+}
+
+__global__ void __launch_bounds__(256) gate_mix_kernel(const float* __restrict__ f3, float* __restrict__ out,
+                                                       int64_t M, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= M * C) return;
+  const int64_t m = idx / C;
+  const int c = (int)(idx - m * C);
+  const float* r = f3 + m * 3 * C;
+  const float g = sigmoid_f(r[c]);
+  out[idx] = g * r[C + c] + (1.0f - g) * r[2 * C + c];
+}
+
+}  // namespace
+
+cudaError_t launch_adaptive_pool(const float* x, int64_t ldx, float* out, int64_t B, int64_t L, int64_t K,
+                                 int C, cudaStream_t s, int64_t* launches) {
+  if (B <= 0 || K <= 0) return cudaSuccess;
+  if (B > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)K, (unsigned)B);
+  adaptive_pool_kernel<<<grid, 256, 0, s>>>(x, ldx, out, L, K, C);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const float* q, int64_t ldq, const float* kv, float* o, int64_t ldo, int64_t B,
+                             int64_t L, int64_t Kk, int heads, int hd, cudaStream_t s, int64_t* launches) {
+  if (B <= 0 || L <= 0) return cudaSuccess;
+  if (hd > ATT_MAX_HD || heads * ATT_TOK > 1024 || B > 65535) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)Kk * 2 * heads * hd * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((L + ATT_TOK - 1) / ATT_TOK), (unsigned)B);
+  attention_kernel<<<grid, heads * ATT_TOK, smem, s>>>(q, ldq, kv, o, ldo, L, Kk, heads, hd);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gate_mix(const float* f3, float* out, int64_t M, int C, cudaStream_t s, int64_t* launches) {
+  if (M <= 0) return cudaSuccess;
+  gate_mix_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, s>>>(f3, out, M, C);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace vasr

@@ -1,0 +1,85 @@
+// ctc.cu — CTC greedy decode on the device (ctc_greedy_decode, velocity_asr/decode.py:27-71):
+// argmax over the vocabulary (ties -> lowest index, as torch.argmax) and the blank/repeat
+// collapse, which the reference does in a host Python loop after a D2H `.tolist()`.
+// Integer work; results are bit-exact by construction.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vasr {
+
+namespace {
+
+// one warp per token row
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int32_t* __restrict__ pred,
+                                                     int64_t M, int V) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* r = logits + m * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int n = lane; n < V; n += 32) {
+    const float v = r[n];
+    if (v > best || (bi == 0x7fffffff)) {  // first element seen always wins; later only strictly greater
+      best = v;
+      bi = n;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if (lane == 0) pred[m] = bi == 0x7fffffff ? 0 : bi;
+}
+
+// one warp per utterance: keep[t] = pred[t] != blank && (!collapse || t == 0 || pred[t] != pred[t-1]).
+// (A blank resets the reference's `prev`, and a blank predecessor differs from any kept token,
+// so comparing with the raw predecessor is the same rule, decode.py:55-66.)
+__global__ void __launch_bounds__(32) ctc_collapse_kernel(const int32_t* __restrict__ pred,
+                                                          int32_t* __restrict__ tokens, int32_t* __restrict__ lens,
+                                                          int64_t L, int blank, int collapse) {
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int32_t* p = pred + b * L;
+  int32_t* out = tokens + b * L;
+  int count = 0;
+  for (int64_t t0 = 0; t0 < L; t0 += 32) {
+    const int64_t t = t0 + lane;
+    int tok = blank;
+    bool keep = false;
+    if (t < L) {
+      tok = p[t];
+      keep = tok != blank && (!collapse || t == 0 || tok != p[t - 1]);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[count + __popc(mask & ((1u << lane) - 1u))] = tok;
+    count += __popc(mask);
+  }
+  for (int64_t t = count + lane; t < L; t += 32) out[t] = -1;
+  if (lane == 0) lens[b] = count;
+}
+
+}  // namespace
+
+cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, cudaStream_t s,
+                          int64_t* launches) {
+  if (M <= 0) return cudaSuccess;
+  argmax_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(logits, pred, M, V);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
+                                int blank, int collapse, cudaStream_t s, int64_t* launches) {
+  if (B <= 0) return cudaSuccess;
+  ctc_collapse_kernel<<<(unsigned)B, 32, 0, s>>>(pred, tokens, lens, L, blank, collapse);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace vasr

@@ -1,0 +1,873 @@
+// engine.cu — the C ABI of libvasr.so (include/vasr.h): handle, weight intake and packing,
+// workspace arena, and the launch sequence of the VELOCITY-ASR v2 inference path
+//   PCM -> log-mel -> temporal binding -> 8 SSM blocks -> global context -> CTC head -> greedy
+// (scripts/transcribe.py:69-82 -> audio.py:65 -> model.py:333-368 -> decode.py:27).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vasr.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace vasr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(VASR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" +   \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + ")");         \
+  } while (0)
+
+#define RET(expr)            \
+  do {                       \
+    int r_ = (expr);         \
+    if (r_ != VASR_OK) return r_; \
+  } while (0)
+
+constexpr int N_FFT = 400, HOP = 160, N_FREQ = 201, PAD = 200;
+constexpr int SPEC_LD = 404;  // 2*201 rounded up to a multiple of 4 (vector stores)
+
+struct BlockW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *conv_w, *conv_b, *A, *D;
+  float *w_in, *w_xdt, *b_xdt, *w_out, *w_f1, *b_f1, *w_f2, *b_f2;
+  int N = 0;
+  int structured = 0;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t bytes = 0;
+  size_t used = 0;
+  void reset() { used = 0; }
+  template <typename T>
+  T* take(int64_t n) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + (size_t)(n > 0 ? n : 0) * sizeof(T);
+    return reinterpret_cast<T*>(base + off);
+  }
+};
+
+}  // namespace
+
+struct vasr_handle {
+  vasr_config cfg{};
+  int device = 0;
+  std::unordered_map<std::string, std::vector<float>> staged;
+  bool committed = false;
+  std::vector<void*> weight_allocs;
+  std::vector<void*> frontend_allocs;
+  std::vector<void*>* alloc_list = &weight_allocs;
+
+  std::vector<BlockW> local, global;
+  float *tb_w = nullptr, *tb_b = nullptr, *pe_time = nullptr, *pe_freq = nullptr, *tb_g = nullptr, *tb_bt = nullptr;
+  int64_t pe_rows = 0;
+  float *loc_g = nullptr, *loc_b = nullptr, *glo_g = nullptr, *glo_b = nullptr;
+  float *p1_w = nullptr, *p1_b = nullptr, *p2_w = nullptr, *p2_b = nullptr;
+  float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;
+  float *w_q = nullptr, *b_q = nullptr, *w_kv = nullptr, *b_kv = nullptr, *w_o = nullptr, *b_o = nullptr;
+  float *w_f3 = nullptr, *b_f3 = nullptr, *w_fo = nullptr, *b_fo = nullptr;
+  float *ctc_g = nullptr, *ctc_b = nullptr, *w_ctc = nullptr, *b_ctc = nullptr;
+  float* dft_w = nullptr;
+  int *fb_lo = nullptr, *fb_off = nullptr;
+  float* fb_w = nullptr;
+
+  Arena ws;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+
+  // timing of the scan launches inside the last transcribe/forward
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  int ev_used = 0;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool ev_total = false;
+};
+
+namespace {
+
+struct Dims {
+  int64_t B, S, T, L, M, K1, K2, Mg, M2, Tp, ldp;
+  int d, di, n_mels, V, att;
+};
+
+Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
+  Dims q{};
+  q.B = B;
+  q.S = S;
+  q.T = T;
+  q.L = (T + 1) / 2;
+  q.M = B * q.L;
+  int64_t k1 = q.L / 8 > 64 ? q.L / 8 : 64;
+  q.K1 = k1 < q.L ? k1 : q.L;
+  int64_t k2 = q.K1 / 4 > 16 ? q.K1 / 4 : 16;
+  k2 = k2 < 64 ? k2 : 64;
+  q.K2 = k2 < q.K1 ? k2 : q.K1;
+  q.Mg = B * q.K1;
+  q.M2 = B * q.K2;
+  q.Tp = T + 2;
+  q.ldp = ((S + 2 * PAD + 3) / 4) * 4;
+  q.d = h->cfg.d_model;
+  q.di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
+  q.n_mels = h->cfg.mel_bins;
+  q.V = h->cfg.vocab_size;
+  q.att = h->cfg.attention_dim;
+  return q;
+}
+
+struct Work {
+  float *xp, *spec, *raw, *mean, *rstd, *melpad;
+  float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
+  float *ga, *gb, *g2, *g2n, *kv;
+  float* logits;
+  int32_t* pred;
+};
+
+// Carves the arena; with measure_only it just computes the size.
+size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w) {
+  Arena a = h->ws;
+  a.reset();
+  Work t{};
+  const int nmax = h->cfg.ssm_state_dim > h->cfg.global_ssm_state_dim ? h->cfg.ssm_state_dim
+                                                                      : h->cfg.global_ssm_state_dim;
+  if (need_mel) {
+    t.xp = a.take<float>(q.B * q.ldp);
+    t.spec = a.take<float>(q.B * q.T * SPEC_LD);
+    t.raw = a.take<float>(q.B * q.T * q.n_mels);
+    t.mean = a.take<float>(q.B * q.n_mels);
+    t.rstd = a.take<float>(q.B * q.n_mels);
+  }
+  t.melpad = a.take<float>(q.B * q.Tp * q.n_mels);
+  t.xa = a.take<float>(q.M * q.d);
+  t.xb = a.take<float>(q.M * q.d);
+  t.u = a.take<float>(q.M * q.d);
+  t.xz = a.take<float>(q.M * 2 * q.di);
+  t.bcdt = a.take<float>(q.M * (2 * nmax + q.di));
+  t.yg = a.take<float>(q.M * q.di);
+  t.hbuf = a.take<float>(q.M * q.di);
+  t.cat = a.take<float>(q.M * 2 * q.d);
+  t.f3 = a.take<float>(q.M * 3 * q.d);
+  t.fm = a.take<float>(q.M * q.d);
+  t.fused = a.take<float>(q.M * q.d);
+  t.qb = a.take<float>(q.M * q.att);
+  t.ob = a.take<float>(q.M * q.att);
+  t.ga = a.take<float>(q.Mg * q.d);
+  t.gb = a.take<float>(q.Mg * q.d);
+  t.g2 = a.take<float>(q.M2 * q.d);
+  t.g2n = a.take<float>(q.M2 * q.d);
+  t.kv = a.take<float>(q.M2 * 2 * q.att);
+  if (need_logits) t.logits = a.take<float>(q.M * q.V);
+  t.pred = a.take<int32_t>(q.M);
+  if (w) *w = t;
+  return a.used + 256;
+}
+
+int ensure_workspace(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w) {
+  const size_t need = carve(h, q, need_mel, need_logits, nullptr);
+  if (need > h->ws.bytes) {
+    CK(cudaDeviceSynchronize());
+    if (h->ws.base) CK(cudaFree(h->ws.base));
+    h->ws.base = nullptr;
+    h->ws.bytes = 0;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, need));
+    h->ws.base = static_cast<char*>(p);
+    h->ws.bytes = need;
+  }
+  carve(h, q, need_mel, need_logits, w);
+  return VASR_OK;
+}
+
+// ---------------------------------------------------------------- weights ---------------
+const std::vector<float>* find(vasr_handle* h, const std::string& k) {
+  auto it = h->staged.find(k);
+  return it == h->staged.end() ? nullptr : &it->second;
+}
+
+int need(vasr_handle* h, const std::string& k, int64_t numel, const std::vector<float>** out) {
+  const std::vector<float>* v = find(h, k);
+  if (!v) return fail(VASR_ERR_STATE, "missing weight: " + k);
+  if (numel >= 0 && (int64_t)v->size() != numel)
+    return fail(VASR_ERR_SHAPE, "weight " + k + " has " + std::to_string(v->size()) + " elements, expected " +
+                                    std::to_string(numel));
+  *out = v;
+  return VASR_OK;
+}
+
+template <typename T>
+int upload(vasr_handle* h, const T* src, size_t n, T** dst) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  h->alloc_list->push_back(p);
+  if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = static_cast<T*>(p);
+  return VASR_OK;
+}
+
+int up(vasr_handle* h, const std::string& k, int64_t numel, float** dst) {
+  const std::vector<float>* v;
+  RET(need(h, k, numel, &v));
+  return upload(h, v->data(), v->size(), dst);
+}
+
+int pack_block(vasr_handle* h, const std::string& p, int N, BlockW* w) {
+  const int d = h->cfg.d_model, di = d * h->cfg.ssm_expand_ratio, ks = h->cfg.ssm_kernel_size;
+  w->N = N;
+  RET(up(h, p + "norm1.weight", d, &w->ln1_g));
+  RET(up(h, p + "norm1.bias", d, &w->ln1_b));
+  RET(up(h, p + "norm2.weight", d, &w->ln2_g));
+  RET(up(h, p + "norm2.bias", d, &w->ln2_b));
+  RET(up(h, p + "conv.weight", (int64_t)d * ks, &w->conv_w));
+  RET(up(h, p + "conv.bias", d, &w->conv_b));
+  const std::vector<float>*alog, *xw, *dw, *db;
+  RET(need(h, p + "ssm.A_log", N, &alog));
+  std::vector<float> A(N);
+  int structured = 1;
+  for (int n = 0; n < N; ++n) {
+    A[n] = -expf((*alog)[n]);
+    if (fabsf((*alog)[n] - logf((float)(n + 1))) > 1e-6f) structured = 0;
+  }
+  w->structured = structured;
+  RET(upload(h, A.data(), A.size(), &w->A));
+  RET(up(h, p + "ssm.D", di, &w->D));
+  RET(up(h, p + "ssm.in_proj.weight", (int64_t)2 * di * d, &w->w_in));
+  RET(need(h, p + "ssm.x_proj.weight", (int64_t)2 * N * di, &xw));
+  RET(need(h, p + "ssm.dt_proj.weight", (int64_t)di * di, &dw));
+  RET(need(h, p + "ssm.dt_proj.bias", di, &db));
+  std::vector<float> wx((size_t)(2 * N + di) * di), bx((size_t)2 * N + di, 0.f);
+  memcpy(wx.data(), xw->data(), xw->size() * sizeof(float));
+  memcpy(wx.data() + xw->size(), dw->data(), dw->size() * sizeof(float));
+  memcpy(bx.data() + 2 * N, db->data(), db->size() * sizeof(float));
+  RET(upload(h, wx.data(), wx.size(), &w->w_xdt));
+  RET(upload(h, bx.data(), bx.size(), &w->b_xdt));
+  RET(up(h, p + "ssm.out_proj.weight", (int64_t)d * di, &w->w_out));
+  RET(up(h, p + "ffn.0.weight", (int64_t)di * d, &w->w_f1));
+  RET(up(h, p + "ffn.0.bias", di, &w->b_f1));
+  RET(up(h, p + "ffn.3.weight", (int64_t)d * di, &w->w_f2));
+  RET(up(h, p + "ffn.3.bias", d, &w->b_f2));
+  return VASR_OK;
+}
+
+// default front-end tables (float32 restatement of audio.py:97, 164-199)
+void default_window(std::vector<float>& w) {
+  w.resize(N_FFT);
+  for (int i = 0; i < N_FFT; ++i) w[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / N_FFT));
+}
+void default_filterbank(int n_mels, std::vector<float>& fb) {
+  fb.assign((size_t)n_mels * N_FREQ, 0.f);
+  auto lin = [](float a, float b, int steps, int i) {
+    float step = (b - a) / (float)(steps - 1);
+    return i < steps / 2 ? a + step * (float)i : b - step * (float)(steps - 1 - i);
+  };
+  const float mel_max = 2595.f * log10f(1.f + 8000.f / 700.f);
+  std::vector<float> hz(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) hz[i] = 700.f * (powf(10.f, lin(0.f, mel_max, n_mels + 2, i) / 2595.f) - 1.f);
+  for (int j = 0; j < n_mels; ++j)
+    for (int k = 0; k < N_FREQ; ++k) {
+      const float f = lin(0.f, 8000.f, N_FREQ, k);
+      const float up_ = (f - hz[j]) / (hz[j + 1] - hz[j] + 1e-10f);
+      const float dn = (hz[j + 2] - f) / (hz[j + 2] - hz[j + 1] + 1e-10f);
+      const float v = up_ < dn ? up_ : dn;
+      fb[(size_t)j * N_FREQ + k] = v > 0.f ? v : 0.f;
+    }
+}
+
+int pack_frontend_impl(vasr_handle* h);
+int pack_frontend(vasr_handle* h) {
+  CK(cudaDeviceSynchronize());
+  for (void* p : h->frontend_allocs) cudaFree(p);
+  h->frontend_allocs.clear();
+  h->alloc_list = &h->frontend_allocs;
+  const int r = pack_frontend_impl(h);
+  h->alloc_list = &h->weight_allocs;
+  return r;
+}
+int pack_frontend_impl(vasr_handle* h) {
+  const int n_mels = h->cfg.mel_bins;
+  std::vector<float> win, fb;
+  if (const std::vector<float>* v = find(h, "frontend.window")) {
+    if ((int)v->size() != N_FFT) return fail(VASR_ERR_SHAPE, "frontend.window must have 400 elements");
+    win = *v;
+  } else {
+    default_window(win);
+  }
+  if (const std::vector<float>* v = find(h, "frontend.mel_filterbank")) {
+    if ((int64_t)v->size() != (int64_t)n_mels * N_FREQ)
+      return fail(VASR_ERR_SHAPE, "frontend.mel_filterbank must be n_mels x 201");
+    fb = *v;
+  } else {
+    default_filterbank(n_mels, fb);
+  }
+  // DFT table rows: k in [0,201): win[n] cos(2 pi k n / 400); 201 + k: win[n] sin(...)
+  std::vector<float> tab((size_t)2 * N_FREQ * N_FFT);
+  for (int k = 0; k < N_FREQ; ++k)
+    for (int n = 0; n < N_FFT; ++n) {
+      const double ang = 2.0 * M_PI * (double)((k * n) % N_FFT) / (double)N_FFT;
+      tab[(size_t)k * N_FFT + n] = (float)((double)win[n] * cos(ang));
+      tab[(size_t)(N_FREQ + k) * N_FFT + n] = (float)((double)win[n] * sin(ang));
+    }
+  RET(upload(h, tab.data(), tab.size(), &h->dft_w));
+  std::vector<int> lo(n_mels), off(n_mels + 1, 0);
+  std::vector<float> wts;
+  for (int j = 0; j < n_mels; ++j) {
+    int a = -1, b = -1;
+    for (int k = 0; k < N_FREQ; ++k)
+      if (fb[(size_t)j * N_FREQ + k] != 0.f) {
+        if (a < 0) a = k;
+        b = k;
+      }
+    lo[j] = a < 0 ? 0 : a;
+    if (a >= 0)
+      for (int k = a; k <= b; ++k) wts.push_back(fb[(size_t)j * N_FREQ + k]);
+    off[j + 1] = (int)wts.size();
+  }
+  RET(upload(h, lo.data(), lo.size(), &h->fb_lo));
+  RET(upload(h, off.data(), off.size(), &h->fb_off));
+  RET(upload(h, wts.data(), wts.size(), &h->fb_w));
+  return VASR_OK;
+}
+
+void free_weights(vasr_handle* h) {
+  for (void* p : h->weight_allocs) cudaFree(p);
+  h->weight_allocs.clear();
+  h->local.clear();
+  h->global.clear();
+  h->committed = false;
+}
+
+// ---------------------------------------------------------------- launch sequences ------
+#define KL(expr)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(e_ == cudaErrorInvalidValue ? VASR_ERR_UNSUPPORTED : VASR_ERR_CUDA,       \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+  } while (0)
+
+int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
+           int64_t M, int64_t K, int64_t N, int act, int act_from, const float* resid, int64_t ldr,
+           cudaStream_t s) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = act_from; g.resid = resid; g.ldr = ldr;
+  KL(launch_gemm(g, s, &h->launches));
+  return VASR_OK;
+}
+
+int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t L, int quirk, cudaStream_t s) {
+  const int di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
+  const int64_t ld = 2 * w.N + di;
+  ScanArgs a;
+  a.x = k.xz; a.ldx = 2 * di;
+  a.z = k.xz + di; a.ldz = 2 * di;
+  a.Bm = k.bcdt; a.ldb = ld;
+  a.Cm = k.bcdt + w.N; a.ldc = ld;
+  a.dt = k.bcdt + 2 * w.N; a.lddt = ld;
+  a.A = w.A; a.D = w.D;
+  a.y = k.yg; a.ldy = di;
+  a.B = B; a.L = L; a.Di = di; a.N = w.N;
+  a.parallel_quirk = quirk;
+  a.structured_a = w.structured;
+  const bool t = h->timing && h->ev_used + 2 <= (int)h->ev.size();
+  if (t) cudaEventRecord(h->ev[h->ev_used], s);
+  KL(launch_selective_scan(a, s, &h->launches));
+  if (t) {
+    cudaEventRecord(h->ev[h->ev_used + 1], s);
+    h->ev_used += 2;
+  }
+  return VASR_OK;
+}
+
+// SSMBlock._forward_impl (ssm.py:404-427): x (M, d) in k.xa -> result in k.xa; xb/u/xz/... scratch
+int run_block(vasr_handle* h, const BlockW& w, const Work& k, float* x, float* x1, int64_t B, int64_t L, int quirk,
+              cudaStream_t s) {
+  const int d = h->cfg.d_model, di = d * h->cfg.ssm_expand_ratio;
+  const int64_t M = B * L;
+  KL(launch_ln_dwconv(x, k.u, w.ln1_g, w.ln1_b, w.conv_w, w.conv_b, B, L, d, h->cfg.ssm_kernel_size, s,
+                      &h->launches));
+  RET(linear(h, k.u, d, w.w_in, nullptr, k.xz, 2 * di, M, d, 2 * di, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.xz, 2 * di, w.w_xdt, w.b_xdt, k.bcdt, 2 * w.N + di, M, di, 2 * w.N + di, ACT_SOFTPLUS, 2 * w.N,
+             nullptr, 0, s));
+  RET(run_scan(h, w, k, B, L, quirk, s));
+  RET(linear(h, k.yg, di, w.w_out, nullptr, x1, d, M, di, d, ACT_NONE, 0, x, d, s));
+  KL(launch_layer_norm(x1, d, k.u, d, w.ln2_g, w.ln2_b, M, d, s, &h->launches));
+  RET(linear(h, k.u, d, w.w_f1, w.b_f1, k.hbuf, di, M, d, di, ACT_GELU, 0, nullptr, 0, s));
+  RET(linear(h, k.hbuf, di, w.w_f2, w.b_f2, x, d, M, di, d, ACT_NONE, 0, x1, d, s));
+  return VASR_OK;
+}
+
+int quirk_for(const vasr_handle* h, int stack, int scan_mode) {
+  if (scan_mode < 0) scan_mode = stack == 0 ? h->cfg.scan_mode : VASR_SCAN_PARALLEL;
+  return scan_mode == VASR_SCAN_PARALLEL ? 1 : 0;
+}
+
+// HierarchicalGlobalContext.forward on local features already in k.cat[:, :d] -> k.fused
+int run_global_context(vasr_handle* h, const Dims& q, const Work& k, cudaStream_t s) {
+  const int d = q.d, att = q.att;
+  KL(launch_adaptive_pool(k.cat, 2 * d, k.gb, q.B, q.L, q.K1, d, s, &h->launches));
+  RET(linear(h, k.gb, d, h->p1_w, h->p1_b, k.ga, d, q.Mg, d, d, ACT_NONE, 0, nullptr, 0, s));
+  for (size_t i = 0; i < h->global.size(); ++i)
+    RET(run_block(h, h->global[i], k, k.ga, k.gb, q.B, q.K1, quirk_for(h, 1, -1), s));
+  KL(launch_layer_norm(k.ga, d, k.ga, d, h->glo_g, h->glo_b, q.Mg, d, s, &h->launches));
+  KL(launch_adaptive_pool(k.ga, d, k.g2, q.B, q.K1, q.K2, d, s, &h->launches));
+  RET(linear(h, k.g2, d, h->p2_w, h->p2_b, k.g2n, d, q.M2, d, d, ACT_NONE, 0, nullptr, 0, s));
+  KL(launch_layer_norm(k.g2n, d, k.g2n, d, h->n1_g, h->n1_b, q.M2, d, s, &h->launches));
+  RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s));
+  KL(launch_layer_norm(k.cat, 2 * d, k.u, d, h->n2_g, h->n2_b, q.M, d, s, &h->launches));
+  RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s));
+  KL(launch_attention(k.qb, att, k.kv, k.ob, att, q.B, q.L, q.K2, h->cfg.attention_heads,
+                      att / h->cfg.attention_heads, s, &h->launches));
+  RET(linear(h, k.ob, att, h->w_o, h->b_o, k.cat + d, 2 * d, q.M, att, d, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s));
+  KL(launch_gate_mix(k.f3, k.fm, q.M, d, s, &h->launches));
+  RET(linear(h, k.fm, d, h->w_fo, h->b_fo, k.fused, d, q.M, d, d, ACT_NONE, 0, nullptr, 0, s));
+  return VASR_OK;
+}
+
+int run_ctc_head(vasr_handle* h, const Dims& q, const Work& k, const float* x, float* logits, cudaStream_t s) {
+  KL(launch_layer_norm(x, q.d, k.u, q.d, h->ctc_g, h->ctc_b, q.M, q.d, s, &h->launches));
+  RET(linear(h, k.u, q.d, h->w_ctc, h->b_ctc, logits, q.V, q.M, q.d, q.V, ACT_NONE, 0, nullptr, 0, s));
+  return VASR_OK;
+}
+
+// padded mel (k.melpad) -> logits
+int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float* f_tb, float* f_local,
+              float* f_fused, cudaStream_t s) {
+  const int d = q.d;
+  if (q.L > h->pe_rows)
+    return fail(VASR_ERR_SHAPE, "sequence of " + std::to_string(q.L) + " tokens exceeds the positional table (" +
+                                    std::to_string(h->pe_rows) + " rows, model.py:87,125)");
+  GemmArgs g;
+  g.A = k.melpad; g.lda = 2 * q.n_mels; g.rows_per_batch = q.L; g.batch_stride = q.Tp * q.n_mels;
+  g.W = h->tb_w; g.bias = h->tb_b; g.C = k.xa; g.ldc = d;
+  g.M = q.M; g.N = d; g.K = 3 * q.n_mels;
+  g.act = ACT_GELU; g.act_from = 0;
+  g.pe_time = h->pe_time; g.pe_freq = h->pe_freq; g.pe_half = d / 2; g.pe_rows = q.L;
+  KL(launch_gemm(g, s, &h->launches));
+  KL(launch_layer_norm(k.xa, d, k.xa, d, h->tb_g, h->tb_bt, q.M, d, s, &h->launches));
+  if (f_tb) CK(cudaMemcpyAsync(f_tb, k.xa, (size_t)q.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  for (size_t i = 0; i < h->local.size(); ++i)
+    RET(run_block(h, h->local[i], k, k.xa, k.xb, q.B, q.L, quirk_for(h, 0, -1), s));
+  KL(launch_layer_norm(k.xa, d, k.cat, 2 * d, h->loc_g, h->loc_b, q.M, d, s, &h->launches));
+  if (f_local)
+    CK(cudaMemcpy2DAsync(f_local, (size_t)d * sizeof(float), k.cat, (size_t)2 * d * sizeof(float),
+                         (size_t)d * sizeof(float), (size_t)q.M, cudaMemcpyDeviceToDevice, s));
+  RET(run_global_context(h, q, k, s));
+  if (f_fused) CK(cudaMemcpyAsync(f_fused, k.fused, (size_t)q.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  RET(run_ctc_head(h, q, k, k.fused, logits, s));
+  return VASR_OK;
+}
+
+// PCM (device) -> k.raw (+ mean/rstd when normalize)
+int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int normalize, cudaStream_t s) {
+  KL(launch_reflect_pad(pcm, k.xp, q.B, q.S, PAD, q.ldp, s, &h->launches));
+  GemmArgs g;
+  g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
+  g.W = h->dft_w; g.C = k.spec; g.ldc = SPEC_LD;
+  g.M = q.B * q.T; g.N = 2 * N_FREQ; g.K = N_FFT;
+  KL(launch_gemm(g, s, &h->launches));
+  KL(launch_mel_log(k.spec, SPEC_LD, k.raw, q.B * q.T, N_FREQ, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, s,
+                    &h->launches));
+  if (normalize) KL(launch_mel_stats(k.raw, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches));
+  return VASR_OK;
+}
+
+int check_ready(const vasr_handle* h) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  if (!h->committed) return fail(VASR_ERR_STATE, "weights not committed (call vasr_commit_weights)");
+  return VASR_OK;
+}
+
+int bind_device(const vasr_handle* h) {
+  CK(cudaSetDevice(h->device));
+  return VASR_OK;
+}
+
+void timing_begin(vasr_handle* h, cudaStream_t s) {
+  h->ev_used = 0;
+  h->ev_total = false;
+  if (h->timing) {
+    cudaEventRecord(h->ev_t0, s);
+    h->ev_total = true;
+  }
+}
+void timing_end(vasr_handle* h, cudaStream_t s) {
+  if (h->timing) cudaEventRecord(h->ev_t1, s);
+}
+
+}  // namespace
+
+// =========================================================================== C ABI =======
+extern "C" {
+
+const char* vasr_last_error(void) { return g_err.c_str(); }
+const char* vasr_version(void) { return "libvasr 0.1 (sm_100a)"; }
+
+int64_t vasr_num_frames(int64_t samples) { return 1 + samples / HOP; }
+int64_t vasr_num_tokens(int64_t frames) { return (frames + 1) / 2; }
+
+int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
+  if (!cfg || !out) return fail(VASR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const vasr_config& c = *cfg;
+  if (c.scan_mode < 0 || c.scan_mode > 2) return fail(VASR_ERR_INVALID, "Unknown scan_mode");
+  if (c.d_model <= 0 || c.d_model > 256 || (c.d_model % 16) != 0)
+    return fail(VASR_ERR_UNSUPPORTED, "d_model must be a multiple of 16, at most 256");
+  if ((c.mel_bins * 3) % 16 != 0 || c.mel_bins * 8 > 1024)
+    return fail(VASR_ERR_UNSUPPORTED, "mel_bins must make 3*mel_bins a multiple of 16 (and be <= 128)");
+  auto n_ok = [](int n) { return n == 16 || n == 32 || n == 64; };
+  if (!n_ok(c.ssm_state_dim) || !n_ok(c.global_ssm_state_dim))
+    return fail(VASR_ERR_UNSUPPORTED, "ssm state_dim must be 16, 32 or 64");
+  const int di = c.d_model * c.ssm_expand_ratio;
+  if (c.ssm_expand_ratio < 1 || (di % 64) != 0) return fail(VASR_ERR_UNSUPPORTED, "d_model*expand_ratio must be a multiple of 64");
+  if (c.ssm_kernel_size < 1 || c.ssm_kernel_size > 8) return fail(VASR_ERR_UNSUPPORTED, "ssm_kernel_size must be in [1, 8]");
+  if (c.attention_heads < 1 || c.attention_dim % c.attention_heads != 0 || c.attention_dim / c.attention_heads > 16 ||
+      c.attention_dim % 16 != 0 || c.attention_heads * 64 > 1024)
+    return fail(VASR_ERR_UNSUPPORTED, "attention_dim must be a multiple of 16 with head_dim <= 16");
+  if (c.vocab_size < 1 || c.ssm_layers < 0 || c.global_ssm_layers < 0) return fail(VASR_ERR_INVALID, "bad sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(VASR_ERR_CUDA, "no CUDA device: libvasr has no CPU path");
+  if (device < 0 || device >= ndev) return fail(VASR_ERR_INVALID, "bad device index");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(VASR_ERR_CUDA, std::string("libvasr is built for sm_100a only; device is ") + prop.name);
+  CK(cudaSetDevice(device));
+  vasr_handle* h = new vasr_handle();
+  h->cfg = c;
+  h->device = device;
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->ev.resize(64);
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreate(&h->ev_t0));
+  CK(cudaEventCreate(&h->ev_t1));
+  RET(pack_frontend(h));
+  *out = h;
+  return VASR_OK;
+}
+
+void vasr_destroy(vasr_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_weights(h);
+  for (void* p : h->frontend_allocs) cudaFree(p);
+  if (h->ws.base) cudaFree(h->ws.base);
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int vasr_set_weight(vasr_handle* h, const char* name, const float* host, int64_t numel) {
+  if (!h || !name || (!host && numel > 0) || numel < 0) return fail(VASR_ERR_INVALID, "null argument");
+  const std::string k(name);
+  static const char* prefixes[] = {"temporal_binding.", "local_ssm.", "global_context.", "ctc_head.", "frontend."};
+  bool ok = false;
+  for (const char* p : prefixes) ok = ok || k.rfind(p, 0) == 0;
+  if (!ok) return fail(VASR_ERR_INVALID, "unknown weight name: " + k);
+  h->staged[k].assign(host, host + numel);
+  if (k.rfind("frontend.", 0) == 0) {  // front-end tables take effect at once, model weights at commit
+    RET(bind_device(h));
+    return pack_frontend(h);
+  }
+  h->committed = false;
+  return VASR_OK;
+}
+
+int vasr_commit_weights(vasr_handle* h) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  RET(bind_device(h));
+  CK(cudaDeviceSynchronize());
+  free_weights(h);
+  const vasr_config& c = h->cfg;
+  const int d = c.d_model, di = d * c.ssm_expand_ratio, nm = c.mel_bins, att = c.attention_dim;
+  // temporal binding: conv.weight (d, mel, 3) -> (d, 3*mel) with k index = tap*mel + channel
+  const std::vector<float>* cw;
+  RET(need(h, "temporal_binding.conv.weight", (int64_t)d * nm * 3, &cw));
+  std::vector<float> tbw((size_t)d * 3 * nm);
+  for (int o = 0; o < d; ++o)
+    for (int ch = 0; ch < nm; ++ch)
+      for (int j = 0; j < 3; ++j) tbw[(size_t)o * 3 * nm + j * nm + ch] = (*cw)[((size_t)o * nm + ch) * 3 + j];
+  RET(upload(h, tbw.data(), tbw.size(), &h->tb_w));
+  RET(up(h, "temporal_binding.conv.bias", d, &h->tb_b));
+  const std::vector<float>* pt;
+  RET(need(h, "temporal_binding.pos_encoding.pe_time", -1, &pt));
+  if (pt->size() % (size_t)(d / 2) != 0) return fail(VASR_ERR_SHAPE, "pe_time must be (rows, d_model/2)");
+  h->pe_rows = (int64_t)pt->size() / (d / 2);
+  RET(upload(h, pt->data(), pt->size(), &h->pe_time));
+  RET(up(h, "temporal_binding.pos_encoding.pe_freq", d - d / 2, &h->pe_freq));
+  RET(up(h, "temporal_binding.norm.weight", d, &h->tb_g));
+  RET(up(h, "temporal_binding.norm.bias", d, &h->tb_bt));
+  h->local.resize(c.ssm_layers);
+  for (int i = 0; i < c.ssm_layers; ++i)
+    RET(pack_block(h, "local_ssm.layers." + std::to_string(i) + ".", c.ssm_state_dim, &h->local[i]));
+  RET(up(h, "local_ssm.norm.weight", d, &h->loc_g));
+  RET(up(h, "local_ssm.norm.bias", d, &h->loc_b));
+  const std::string gc = "global_context.";
+  h->global.resize(c.global_ssm_layers);
+  for (int i = 0; i < c.global_ssm_layers; ++i)
+    RET(pack_block(h, gc + "global_ssm.layers." + std::to_string(i) + ".", c.global_ssm_state_dim, &h->global[i]));
+  RET(up(h, gc + "global_ssm.norm.weight", d, &h->glo_g));
+  RET(up(h, gc + "global_ssm.norm.bias", d, &h->glo_b));
+  RET(up(h, gc + "pool1.pool_proj.weight", (int64_t)d * d, &h->p1_w));
+  RET(up(h, gc + "pool1.pool_proj.bias", d, &h->p1_b));
+  RET(up(h, gc + "pool2.pool_proj.weight", (int64_t)d * d, &h->p2_w));
+  RET(up(h, gc + "pool2.pool_proj.bias", d, &h->p2_b));
+  RET(up(h, gc + "norm1.weight", d, &h->n1_g));
+  RET(up(h, gc + "norm1.bias", d, &h->n1_b));
+  RET(up(h, gc + "norm2.weight", d, &h->n2_g));
+  RET(up(h, gc + "norm2.bias", d, &h->n2_b));
+  RET(up(h, gc + "cross_attention.q_proj.weight", (int64_t)att * d, &h->w_q));
+  RET(up(h, gc + "cross_attention.q_proj.bias", att, &h->b_q));
+  const std::vector<float>*kw, *kb, *vw, *vb;
+  RET(need(h, gc + "cross_attention.k_proj.weight", (int64_t)att * d, &kw));
+  RET(need(h, gc + "cross_attention.k_proj.bias", att, &kb));
+  RET(need(h, gc + "cross_attention.v_proj.weight", (int64_t)att * d, &vw));
+  RET(need(h, gc + "cross_attention.v_proj.bias", att, &vb));
+  std::vector<float> wkv(*kw), bkv(*kb);
+  wkv.insert(wkv.end(), vw->begin(), vw->end());
+  bkv.insert(bkv.end(), vb->begin(), vb->end());
+  RET(upload(h, wkv.data(), wkv.size(), &h->w_kv));
+  RET(upload(h, bkv.data(), bkv.size(), &h->b_kv));
+  RET(up(h, gc + "cross_attention.out_proj.weight", (int64_t)d * att, &h->w_o));
+  RET(up(h, gc + "cross_attention.out_proj.bias", d, &h->b_o));
+  // fusion: one (3d x 2d) projection of [local | ctx]: gate rows, then local_proj on the left
+  // half, then global_proj on the right half (zeros elsewhere).
+  const std::vector<float>*gw, *gb, *lw, *lb, *cw2, *cb2;
+  RET(need(h, gc + "fusion.gate_proj.0.weight", (int64_t)d * 2 * d, &gw));
+  RET(need(h, gc + "fusion.gate_proj.0.bias", d, &gb));
+  RET(need(h, gc + "fusion.local_proj.weight", (int64_t)d * d, &lw));
+  RET(need(h, gc + "fusion.local_proj.bias", d, &lb));
+  RET(need(h, gc + "fusion.global_proj.weight", (int64_t)d * d, &cw2));
+  RET(need(h, gc + "fusion.global_proj.bias", d, &cb2));
+  std::vector<float> wf3((size_t)3 * d * 2 * d, 0.f), bf3;
+  memcpy(wf3.data(), gw->data(), gw->size() * sizeof(float));
+  for (int o = 0; o < d; ++o) {
+    memcpy(&wf3[(size_t)(d + o) * 2 * d], &(*lw)[(size_t)o * d], d * sizeof(float));
+    memcpy(&wf3[(size_t)(2 * d + o) * 2 * d + d], &(*cw2)[(size_t)o * d], d * sizeof(float));
+  }
+  bf3 = *gb;
+  bf3.insert(bf3.end(), lb->begin(), lb->end());
+  bf3.insert(bf3.end(), cb2->begin(), cb2->end());
+  RET(upload(h, wf3.data(), wf3.size(), &h->w_f3));
+  RET(upload(h, bf3.data(), bf3.size(), &h->b_f3));
+  RET(up(h, gc + "fusion.out_proj.weight", (int64_t)d * d, &h->w_fo));
+  RET(up(h, gc + "fusion.out_proj.bias", d, &h->b_fo));
+  RET(up(h, "ctc_head.proj.0.weight", d, &h->ctc_g));
+  RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
+  RET(up(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &h->w_ctc));
+  RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
+  (void)di;
+  h->committed = true;
+  return VASR_OK;
+}
+
+int vasr_log_mel(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int normalize, float* mel_dev,
+                 void* stream) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  if (B < 0 || !pcm_dev || !mel_dev) return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims q = make_dims(h, B, S, vasr_num_frames(S));
+  Work k;
+  RET(ensure_workspace(h, q, true, false, &k));
+  RET(run_mel(h, q, k, pcm_dev, normalize, s));
+  KL(launch_mel_finish(k.raw, normalize ? k.mean : nullptr, k.rstd, mel_dev, q.B, q.T, q.n_mels, q.T, 0, s,
+                       &h->launches));
+  return VASR_OK;
+}
+
+int vasr_forward(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, float* logits_dev, float* feat_tb_dev,
+                 float* feat_local_dev, float* feat_fused_dev, void* stream) {
+  RET(check_ready(h));
+  if (B < 0 || T < 1 || !mel_dev || !logits_dev) return fail(VASR_ERR_INVALID, "null argument");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims q = make_dims(h, B, 0, T);
+  Work k;
+  RET(ensure_workspace(h, q, false, false, &k));
+  timing_begin(h, s);
+  KL(launch_mel_finish(mel_dev, nullptr, nullptr, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches));
+  RET(run_model(h, q, k, logits_dev, feat_tb_dev, feat_local_dev, feat_fused_dev, s));
+  timing_end(h, s);
+  return VASR_OK;
+}
+
+int vasr_ssm_block(vasr_handle* h, int stack, int layer, int scan_mode, const float* x_dev, int64_t B, int64_t L,
+                   float* out_dev, void* stream) {
+  RET(check_ready(h));
+  if (stack < 0 || stack > 1) return fail(VASR_ERR_INVALID, "stack must be 0 (local) or 1 (global)");
+  const std::vector<BlockW>& blocks = stack == 0 ? h->local : h->global;
+  if (layer < 0 || layer >= (int)blocks.size()) return fail(VASR_ERR_INVALID, "layer out of range");
+  if (scan_mode > 2) return fail(VASR_ERR_INVALID, "Unknown scan_mode");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Dims q = make_dims(h, B, 0, 2 * L - 1);
+  Work k;
+  RET(ensure_workspace(h, q, false, false, &k));
+  const size_t bytes = (size_t)B * L * q.d * sizeof(float);
+  CK(cudaMemcpyAsync(k.xa, x_dev, bytes, cudaMemcpyDeviceToDevice, s));
+  RET(run_block(h, blocks[layer], k, k.xa, k.xb, B, L, quirk_for(h, stack, scan_mode), s));
+  CK(cudaMemcpyAsync(out_dev, k.xa, bytes, cudaMemcpyDeviceToDevice, s));
+  return VASR_OK;
+}
+
+int vasr_global_context(vasr_handle* h, const float* local_dev, int64_t B, int64_t L, float* out_dev, void* stream) {
+  RET(check_ready(h));
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Dims q = make_dims(h, B, 0, 2 * L - 1);
+  Work k;
+  RET(ensure_workspace(h, q, false, false, &k));
+  const size_t row = (size_t)q.d * sizeof(float);
+  CK(cudaMemcpy2DAsync(k.cat, 2 * row, local_dev, row, row, (size_t)q.M, cudaMemcpyDeviceToDevice, s));
+  RET(run_global_context(h, q, k, s));
+  CK(cudaMemcpyAsync(out_dev, k.fused, (size_t)q.M * row, cudaMemcpyDeviceToDevice, s));
+  return VASR_OK;
+}
+
+int vasr_ctc_head(vasr_handle* h, const float* x_dev, int64_t B, int64_t L, float* logits_dev, void* stream) {
+  RET(check_ready(h));
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Dims q = make_dims(h, B, 0, 2 * L - 1);
+  Work k;
+  RET(ensure_workspace(h, q, false, false, &k));
+  RET(run_ctc_head(h, q, k, x_dev, logits_dev, s));
+  return VASR_OK;
+}
+
+int vasr_selective_scan(const float* x, int64_t ldx, const float* dt, int64_t lddt, const float* A, const float* Bm,
+                        int64_t ldb, const float* Cm, int64_t ldc, const float* D, const float* z, int64_t ldz,
+                        float* y, int64_t ldy, int64_t B, int64_t L, int64_t Di, int64_t N, int scan_mode,
+                        void* stream) {
+  if (!x || !dt || !A || !Bm || !Cm || !y) return fail(VASR_ERR_INVALID, "null argument");
+  if (scan_mode < 0 || scan_mode > 2) return fail(VASR_ERR_INVALID, "Unknown scan_mode");
+  if (N != 16 && N != 32 && N != 64) return fail(VASR_ERR_UNSUPPORTED, "state_dim must be 16, 32 or 64");
+  float ah[64];
+  CK(cudaMemcpy(ah, A, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
+  int structured = 1;
+  for (int n = 0; n < N; ++n)
+    if (fabsf(ah[n] + (float)(n + 1)) > 2e-6f * (float)(n + 1)) structured = 0;
+  ScanArgs a;
+  a.x = x; a.ldx = ldx; a.dt = dt; a.lddt = lddt; a.z = z; a.ldz = ldz;
+  a.Bm = Bm; a.ldb = ldb; a.Cm = Cm; a.ldc = ldc; a.A = A; a.D = D; a.y = y; a.ldy = ldy;
+  a.B = B; a.L = L; a.Di = (int)Di; a.N = (int)N;
+  a.parallel_quirk = scan_mode == VASR_SCAN_PARALLEL;
+  a.structured_a = structured;
+  KL(launch_selective_scan(a, static_cast<cudaStream_t>(stream), nullptr));
+  return VASR_OK;
+}
+
+int vasr_ctc_greedy(const float* logits_dev, int64_t B, int64_t L, int64_t V, int blank, int collapse,
+                    int32_t* tokens_dev, int32_t* lens_dev, void* stream) {
+  if (!tokens_dev || !lens_dev || (!logits_dev && B * L > 0)) return fail(VASR_ERR_INVALID, "null argument");
+  if (B <= 0) return VASR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t* pred = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&pred), (size_t)(B * L > 0 ? B * L : 1) * sizeof(int32_t), s));
+  KL(launch_argmax(logits_dev, pred, B * L, (int)V, s, nullptr));
+  KL(launch_ctc_collapse(pred, tokens_dev, lens_dev, B, L, blank, collapse, s, nullptr));
+  CK(cudaFreeAsync(pred, s));
+  return VASR_OK;
+}
+
+int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int32_t* tokens_dev,
+                    int32_t* lens_dev, void* stream) {
+  RET(check_ready(h));
+  if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev) return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims q = make_dims(h, B, S, vasr_num_frames(S));
+  Work k;
+  RET(ensure_workspace(h, q, true, true, &k));
+  timing_begin(h, s);
+  RET(run_mel(h, q, k, pcm_dev, 1, s));
+  KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches));
+  RET(run_model(h, q, k, k.logits, nullptr, nullptr, nullptr, s));
+  KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));
+  KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches));
+  timing_end(h, s);
+  return VASR_OK;
+}
+
+int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64_t S, int32_t* tokens_host,
+                         int32_t* lens_host) {
+  RET(check_ready(h));
+  if (B <= 0 || !pcm_host || !tokens_host || !lens_host) return fail(VASR_ERR_INVALID, "null argument");
+  RET(bind_device(h));
+  const int64_t L = vasr_num_tokens(vasr_num_frames(S));
+  cudaStream_t s = h->own_stream;
+  float* pcm = nullptr;
+  int32_t *tok = nullptr, *len = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&pcm), (size_t)B * S * sizeof(float), s));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&tok), (size_t)B * L * sizeof(int32_t), s));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&len), (size_t)B * sizeof(int32_t), s));
+  CK(cudaMemcpyAsync(pcm, pcm_host, (size_t)B * S * sizeof(float), cudaMemcpyHostToDevice, s));
+  int r = vasr_transcribe(h, pcm, B, S, tok, len, s);
+  if (r == VASR_OK) {
+    CK(cudaMemcpyAsync(tokens_host, tok, (size_t)B * L * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(lens_host, len, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  cudaFreeAsync(pcm, s);
+  cudaFreeAsync(tok, s);
+  cudaFreeAsync(len, s);
+  CK(cudaStreamSynchronize(s));
+  return r;
+}
+
+int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev, float* out_dev,
+                int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream) {
+  if (!x_dev || !w_dev || !out_dev) return fail(VASR_ERR_INVALID, "null argument");
+  if (act < 0 || act > 3) return fail(VASR_ERR_INVALID, "unknown activation");
+  GemmArgs g;
+  g.A = x_dev; g.lda = ldx; g.W = w_dev; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
+  KL(launch_gemm(g, static_cast<cudaStream_t>(stream), nullptr));
+  return VASR_OK;
+}
+
+int64_t vasr_kernel_launches(const vasr_handle* h) { return h ? h->launches : 0; }
+int64_t vasr_workspace_bytes(const vasr_handle* h) { return h ? (int64_t)h->ws.bytes : 0; }
+
+int vasr_set_timing(vasr_handle* h, int enabled) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  h->timing = enabled != 0;
+  return VASR_OK;
+}
+
+int vasr_last_timing(const vasr_handle* h, float* scan_ms, int32_t* scan_launches, float* total_ms) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  if (!h->ev_total) return fail(VASR_ERR_STATE, "timing was not enabled for the last call");
+  CK(cudaEventSynchronize(h->ev_t1));
+  float tot = 0.f, sc = 0.f;
+  CK(cudaEventElapsedTime(&tot, h->ev_t0, h->ev_t1));
+  for (int i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    sc += ms;
+  }
+  if (scan_ms) *scan_ms = sc;
+  if (scan_launches) *scan_launches = h->ev_used / 2;
+  if (total_ms) *total_ms = tot;
+  return VASR_OK;
+}
+
+}  // extern "C"

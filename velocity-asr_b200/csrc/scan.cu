@@ -1,0 +1,284 @@
+// scan.cu — selective scan (SelectiveSSM._sequential_scan / _mamba_scan / _parallel_scan,
+// velocity_asr/ssm.py:134-337), with the D skip (ssm.py:170,213) and the silu(z) gate
+// (ssm.py:129) fused into the same pass.
+//
+//   h[d,n] <- exp(dt[t,d] A[n]) h[d,n] + x[t,d] dt[t,d] B[t,n];   y[t,d] = sum_n h[d,n] C[t,n] + x[t,d] D[d]
+//
+// Mapping.  A (b, d) row is sequential in t and is owned by LPR = N/8 lanes of one warp; each
+// lane keeps 8 states in registers as four packed fp32x2 values, so the whole update runs on
+// FFMA2/FMUL2 (two state updates per issue slot).  The partial dot products <h, C> of eight
+// consecutive timesteps are reduced across the LPR lanes with one transpose-reduce (7 shuffles
+// per 8 steps for N = 64 instead of 24), which leaves each lane holding the finished y of one
+// (or two) timesteps: that lane applies the D skip and the gate.  All rows of a CTA belong to
+// one utterance, so the B/C rows of a 32-step chunk are staged once in shared memory and read
+// by every row as broadcast 16-byte loads; x/dt/z/y tiles go through shared memory too so
+// global accesses are contiguous runs per timestep.
+//
+// Structured A.  The reference never re-initialises A_log (model.py:305-318), so A[n] = -(n+1)
+// in every random-init model (ssm.py:83-84).  Then exp(dt A[n]) = r^(n+1) with r = exp(-dt):
+// two MUFU ops per lane-step plus a packed multiply chain instead of one MUFU per state.
+// The generic path (one ex2 per state) is kept for trained checkpoints.
+//
+// 'parallel' quirk.  The reference's default scan (ssm.py:228-295) is an exclusive scan with a
+// mis-ordered down-sweep combine.  It equals (oracle/velocity_oracle.py
+// scan_parallel_streaming), with H[e] the true state after e steps, S[e] = sum_{s<e} dt_s and
+// parent(t) = t & (t-1):
+//     hP[0] = 0;  hP[t] = hP[parent] + exp(A S[t]) * (H[t] - exp(A (S[t]-S[parent])) H[parent])
+// which is evaluated left to right with O(log L) saved ancestors per state.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vasr {
+
+namespace {
+
+constexpr int SPL = 8;             // states per lane
+constexpr int TC = 32;             // timesteps per staged chunk
+constexpr int SCAN_THREADS = 128;
+constexpr int NLEV = 26;           // ancestor levels of the quirk mode (L < 2^24)
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct State8 {
+  u64 v[4];
+};
+
+// p[k] = r^(n0 + k + 1), r = 2^s  (s = -dt * log2 e)
+__device__ __forceinline__ void powers_structured(float s, float n0p1, State8& p) {
+  const float r1 = ex2_approx(s);
+  const float e1 = ex2_approx(s * n0p1);
+  const float r2 = r1 * r1;
+  const u64 rr = pack2(r2, r2);
+  p.v[0] = pack2(e1, e1 * r1);
+  p.v[1] = mul2(p.v[0], rr);
+  p.v[2] = mul2(p.v[1], rr);
+  p.v[3] = mul2(p.v[2], rr);
+}
+// p[k] = 2^(s * al2[k]),  al2[k] = A[n0+k] * log2 e  (negative), s = dt >= 0
+__device__ __forceinline__ void powers_generic(float s, const float (&al2)[SPL], State8& p) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p.v[k] = pack2(ex2_approx(s * al2[2 * k]), ex2_approx(s * al2[2 * k + 1]));
+}
+
+template <int LPR, bool QUIRK, bool STRUCT>
+__global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a) {
+  constexpr int N = LPR * SPL;
+  constexpr int ROWS = SCAN_THREADS / LPR;
+  constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : (LPR == 2 ? 1 : 0));
+  constexpr int TPL = 8 >> NR;  // finished timesteps per lane after the transpose-reduce
+
+  __shared__ __align__(16) float sB[TC][N];
+  __shared__ __align__(16) float sC[TC][N];
+  __shared__ float sx[TC][ROWS];
+  __shared__ float sdt[TC][ROWS];
+  __shared__ float sz[TC][ROWS];
+  __shared__ float sy[TC][ROWS];
+
+  const int tid = threadIdx.x;
+  const int rl = tid / LPR;   // row within the CTA
+  const int j = tid % LPR;    // lane within the row
+  const int n0 = j * SPL;
+  const int d0 = blockIdx.x * ROWS;
+  const int64_t b = blockIdx.y;
+  const int64_t L = a.L;
+  const bool gate = a.z != nullptr;
+
+  float al2[SPL];
+#pragma unroll
+  for (int k = 0; k < SPL; ++k) al2[k] = a.A[n0 + k] * LOG2E;
+  const float n0p1 = (float)(n0 + 1);
+  const float Dd = a.D ? a.D[d0 + rl] : 0.f;
+
+  State8 H;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) H.v[k] = 0ull;
+
+  // quirk-mode ancestors (local memory; touched ~2 levels per step)
+  float anc_hp[QUIRK ? NLEV : 1][SPL];
+  float anc_H[QUIRK ? NLEV : 1][SPL];
+  double anc_S[QUIRK ? NLEV : 1];
+  double S = 0.0;
+  if (QUIRK) {
+    for (int l = 0; l < NLEV; ++l) {
+      anc_S[l] = 0.0;
+#pragma unroll
+      for (int k = 0; k < SPL; ++k) anc_hp[l][k] = anc_H[l][k] = 0.f;
+    }
+  }
+
+  for (int64_t tc0 = 0; tc0 < L; tc0 += TC) {
+    const int tcn = (int)((L - tc0) < TC ? (L - tc0) : TC);
+    // ---- stage the chunk
+    for (int idx = tid; idx < TC * (N / 4); idx += SCAN_THREADS) {
+      const int t = idx / (N / 4), c4 = (idx % (N / 4)) * 4;
+      float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vc = vb;
+      if (t < tcn) {
+        const int64_t row = b * L + tc0 + t;
+        vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + c4));
+        vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + c4));
+      }
+      *reinterpret_cast<float4*>(&sB[t][c4]) = vb;
+      *reinterpret_cast<float4*>(&sC[t][c4]) = vc;
+    }
+    for (int idx = tid; idx < TC * ROWS; idx += SCAN_THREADS) {
+      const int t = idx / ROWS, r = idx % ROWS;
+      float vx = 0.f, vd = 0.f, vz = 0.f;
+      if (t < tcn) {
+        const int64_t row = b * L + tc0 + t;
+        vx = __ldg(a.x + row * a.ldx + d0 + r);
+        vd = __ldg(a.dt + row * a.lddt + d0 + r);
+        if (gate) vz = __ldg(a.z + row * a.ldz + d0 + r);
+      }
+      sx[t][r] = vx;
+      sdt[t][r] = vd;
+      sz[t][r] = vz;
+    }
+    __syncthreads();
+
+    // ---- eight timesteps at a time
+    for (int g8 = 0; g8 < TC; g8 += 8) {
+      if (g8 >= tcn) break;
+      float yp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = g8 + i;
+        const float dtv = sdt[t][rl];
+        const float xv = sx[t][rl];
+        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][n0]);
+        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][n0 + 4]);
+
+        if (QUIRK) {
+          const int64_t tg = tc0 + t;
+          State8 hp;
+          if (tg == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hp.v[k] = 0ull;
+          } else {
+            const int tz = __ffsll((long long)tg) - 1;
+            const int pl = tz + 1;
+            const float Sf = (float)S;
+            const float dS = (float)(S - anc_S[pl]);
+            State8 q, pd;
+            if (STRUCT) {
+              powers_structured(-Sf * LOG2E, n0p1, q);
+              powers_structured(-dS * LOG2E, n0p1, pd);
+            } else {
+              powers_generic(Sf, al2, q);
+              powers_generic(dS, al2, pd);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const u64 npH = pack2(-anc_H[pl][2 * k], -anc_H[pl][2 * k + 1]);
+              const u64 php = pack2(anc_hp[pl][2 * k], anc_hp[pl][2 * k + 1]);
+              // inner = H - pd * pH ; hp = php + q * inner
+              const u64 inner = fma2(pd.v[k], npH, H.v[k]);
+              hp.v[k] = fma2(q.v[k], inner, php);
+            }
+            for (int l = 0; l <= tz; ++l) {
+              anc_S[l] = S;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                unpack2(hp.v[k], anc_hp[l][2 * k], anc_hp[l][2 * k + 1]);
+                unpack2(H.v[k], anc_H[l][2 * k], anc_H[l][2 * k + 1]);
+              }
+            }
+          }
+          u64 acc = mul2(hp.v[0], c01.x);
+          acc = fma2(hp.v[1], c01.y, acc);
+          acc = fma2(hp.v[2], c23.x, acc);
+          acc = fma2(hp.v[3], c23.y, acc);
+          yp[i] = hsum2(acc);
+          S += (double)dtv;
+        }
+
+        // true recurrence step: H <- p * H + (x dt) * B
+        State8 p;
+        if (STRUCT) powers_structured(-dtv * LOG2E, n0p1, p);
+        else powers_generic(dtv, al2, p);
+        const float u = xv * dtv;
+        const u64 uu = pack2(u, u);
+        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[t][n0]);
+        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[t][n0 + 4]);
+        H.v[0] = fma2(p.v[0], H.v[0], mul2(uu, b01.x));
+        H.v[1] = fma2(p.v[1], H.v[1], mul2(uu, b01.y));
+        H.v[2] = fma2(p.v[2], H.v[2], mul2(uu, b23.x));
+        H.v[3] = fma2(p.v[3], H.v[3], mul2(uu, b23.y));
+        if (!QUIRK) {
+          u64 acc = mul2(H.v[0], c01.x);
+          acc = fma2(H.v[1], c01.y, acc);
+          acc = fma2(H.v[2], c23.x, acc);
+          acc = fma2(H.v[3], c23.y, acc);
+          yp[i] = hsum2(acc);
+        }
+      }
+
+      // ---- transpose-reduce over the LPR lanes of the row
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int lane_bit = LPR >> (r + 1);
+        const int cnt = 4 >> r;
+        const bool hi = (j & lane_bit) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const float mine = hi ? yp[i + cnt] : yp[i];
+          const float other = hi ? yp[i] : yp[i + cnt];
+          yp[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
+        }
+      }
+      // lane j now owns timesteps g8 + j*TPL + i, i < TPL: skip term, gate, stage for the store
+#pragma unroll
+      for (int i = 0; i < TPL; ++i) {
+        const int t = g8 + j * TPL + i;
+        float yv = yp[i] + sx[t][rl] * Dd;
+        if (gate) {
+          const float zv = sz[t][rl];
+          yv *= zv / (1.0f + __expf(-zv));
+        }
+        sy[t][rl] = yv;
+      }
+    }
+    __syncthreads();
+    // ---- store the chunk
+    for (int idx = tid; idx < tcn * ROWS; idx += SCAN_THREADS) {
+      const int t = idx / ROWS, r = idx % ROWS;
+      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
+    }
+    // the next chunk's staging does not touch sy, and its first __syncthreads orders the
+    // sy reads above before the next writes to sy.
+  }
+}
+
+template <int LPR>
+cudaError_t launch_lpr(const ScanArgs& a, cudaStream_t s) {
+  constexpr int ROWS = SCAN_THREADS / LPR;
+  if (a.Di % ROWS != 0) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)(a.Di / ROWS), (unsigned)a.B);
+  if (a.parallel_quirk) {
+    if (a.structured_a) selective_scan_kernel<LPR, true, true><<<grid, SCAN_THREADS, 0, s>>>(a);
+    else selective_scan_kernel<LPR, true, false><<<grid, SCAN_THREADS, 0, s>>>(a);
+  } else {
+    if (a.structured_a) selective_scan_kernel<LPR, false, true><<<grid, SCAN_THREADS, 0, s>>>(a);
+    else selective_scan_kernel<LPR, false, false><<<grid, SCAN_THREADS, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* launches) {
+  if (a.B <= 0 || a.L <= 0) return cudaSuccess;
+  if (a.B > 65535 || a.L >= (1LL << (NLEV - 2))) return cudaErrorInvalidValue;
+  if ((a.ldb & 3) || (a.ldc & 3) || (reinterpret_cast<uintptr_t>(a.Bm) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.Cm) & 15))
+    return cudaErrorInvalidValue;
+  cudaError_t e;
+  switch (a.N) {
+    case 64: e = launch_lpr<8>(a, s); break;
+    case 32: e = launch_lpr<4>(a, s); break;
+    case 16: e = launch_lpr<2>(a, s); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (launches && e == cudaSuccess) ++*launches;
+  return e;
+}
+
+}  // namespace vasr

@@ -1,0 +1,74 @@
+"""CTC decoding: ctc_greedy_decode / CTCDecoder / create_default_vocabulary of
+velocity_asr/decode.py, with the argmax and the blank/repeat collapse done on the GPU."""
+import ctypes
+from typing import List
+
+import torch
+
+from . import _native
+
+BLANK_TOKEN = 0  # decode.py:14
+
+
+def ctc_greedy_decode(logits: torch.Tensor, blank_token: int = BLANK_TOKEN,
+                      collapse_repeated: bool = True) -> List[List[int]]:
+    """logits (B, L, V) on a CUDA device -> token-id lists.  Same rule as decode.py:46-69:
+    argmax (ties -> lowest index), drop blanks, collapse repeats, a blank resets the repeat state."""
+    if logits.dim() != 3:
+        raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
+    if logits.device.type != "cuda":
+        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    B, L, V = logits.shape
+    if B == 0:
+        return []
+    if L == 0:
+        return [[] for _ in range(B)]
+    lg = logits.to(torch.float32).contiguous()
+    tokens = torch.empty(B, L, dtype=torch.int32, device=lg.device)
+    lens = torch.empty(B, dtype=torch.int32, device=lg.device)
+    lib = _native.lib()
+    with torch.cuda.device(lg.device):
+        _native.check(lib.vasr_ctc_greedy(_native.ptr(lg), B, L, V, int(blank_token), int(bool(collapse_repeated)),
+                                          _native.ptr(tokens), _native.ptr(lens),
+                                          ctypes.c_void_p(torch.cuda.current_stream(lg.device).cuda_stream)))
+    tokens, lens = tokens.cpu(), lens.cpu()
+    return [tokens[b, : int(lens[b])].tolist() for b in range(B)]
+
+
+class CTCDecoder:
+    """decode.py:220-328 (greedy path): vocabulary lookup around ctc_greedy_decode."""
+
+    def __init__(self, vocabulary: List[str], blank_token: int = BLANK_TOKEN):
+        self.vocabulary = vocabulary
+        self.blank_token = blank_token
+        self.vocab_size = len(vocabulary)
+        self.token_to_idx = {tok: i for i, tok in enumerate(vocabulary)}
+
+    def decode_greedy(self, logits: torch.Tensor, collapse_repeated: bool = True) -> List[str]:
+        seqs = ctc_greedy_decode(logits, blank_token=self.blank_token, collapse_repeated=collapse_repeated)
+        return [self._tokens_to_text(s) for s in seqs]
+
+    def _tokens_to_text(self, tokens: List[int]) -> str:
+        """decode.py:302-317: join, then turn the subword marker into spaces."""
+        pieces = [self.vocabulary[t] if 0 <= t < self.vocab_size else "<unk>" for t in tokens]
+        return "".join(pieces).replace("▁", " ").strip()
+
+    def text_to_tokens(self, text: str) -> List[int]:
+        unk = self.token_to_idx.get("<unk>")
+        out = []
+        for ch in text:
+            if ch in self.token_to_idx:
+                out.append(self.token_to_idx[ch])
+            elif unk is not None:
+                out.append(unk)
+        return out
+
+
+def create_default_vocabulary(vocab_size: int = 50000) -> List[str]:
+    """decode.py:330-362: specials, space, a-z, A-Z, 0-9, punctuation, then <token_i> fillers."""
+    import string
+    vocab = ["<blank>", "<unk>", "<pad>", " "]
+    vocab += list(string.ascii_lowercase) + list(string.ascii_uppercase) + list(string.digits)
+    vocab += list(".,!?;:'\"()-")
+    vocab += [f"<token_{i}>" for i in range(len(vocab), vocab_size)]
+    return vocab

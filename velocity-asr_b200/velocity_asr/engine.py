@@ -1,0 +1,221 @@
+"""VELOCITYASR — the reference's model class (velocity_asr/model.py:242-471) as a thin host
+object: parameters live in a torch module tree with the reference's state_dict keys; forward()
+runs entirely in libvasr.so (hand-written sm_100a kernels) through the C ABI."""
+import ctypes
+import os
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .config import SCAN_MODES, VelocityASRConfig
+from .params import build_parameter_tree, reference_init_, time_table
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Engine:
+    """Owns one vasr_handle (one GPU).  Re-uploads weights when the parameters change."""
+
+    def __init__(self, cfg: VelocityASRConfig, device: torch.device):
+        self.device = device
+        self.lib = _native.lib()
+        c = _native.VasrConfig(
+            cfg.mel_bins, cfg.d_model, cfg.ssm_layers, cfg.ssm_state_dim, cfg.ssm_expand_ratio,
+            cfg.ssm_kernel_size, cfg.global_ssm_layers, cfg.global_ssm_state_dim, cfg.attention_heads,
+            cfg.attention_dim, cfg.vocab_size, _native.SCAN_MODE_ID[cfg.scan_mode])
+        self.handle = ctypes.c_void_p()
+        _native.check(self.lib.vasr_create(ctypes.byref(c), device.index or 0, ctypes.byref(self.handle)))
+        self.fingerprint = None
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.vasr_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync_weights(self, state: Dict[str, torch.Tensor], extra: Dict[str, torch.Tensor]):
+        fp = tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
+        if fp == self.fingerprint:
+            return
+        for k, v in list(state.items()) + list(extra.items()):
+            host = v.detach().to("cpu", torch.float32).contiguous()
+            _native.check(self.lib.vasr_set_weight(self.handle, k.encode(), _native.ptr(host), host.numel()))
+        _native.check(self.lib.vasr_commit_weights(self.handle))
+        self.fingerprint = fp
+
+
+class VELOCITYASR(nn.Module):
+    """Drop-in for velocity_asr.VELOCITYASR (model.py:242).  Same constructor, state_dict,
+    forward(mel, return_features), get_output_length, from_pretrained / save_pretrained,
+    count_parameters; plus transcribe(audio) for the fused PCM -> tokens path.
+
+    Inference only (the reference's callers run it under eval() + no_grad(),
+    scripts/transcribe.py:76,225); dropout is the identity.  CUDA only: there is no CPU path.
+    """
+
+    def __init__(self, config: Optional[VelocityASRConfig] = None):
+        super().__init__()
+        if config is None:
+            config = VelocityASRConfig()
+        if config.scan_mode not in SCAN_MODES:
+            raise ValueError(f"Unknown scan_mode: {config.scan_mode}")
+        self.config = config
+        build_parameter_tree(self, config)
+        reference_init_(self)
+        self._engines: Dict[int, _Engine] = {}
+
+    # ---- native plumbing ------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        return self.temporal_binding.conv.weight.device
+
+    def _engine(self, device: torch.device) -> _Engine:
+        if device.type != "cuda":
+            raise RuntimeError(
+                "velocity_asr (B200 build) runs on CUDA only: move the model and its input to a "
+                "CUDA device (model.to('cuda')); there is no CPU fallback")
+        if self.config.scan_mode not in SCAN_MODES:
+            raise ValueError(f"Unknown scan_mode: {self.config.scan_mode}")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        device = torch.device("cuda", idx)
+        eng = self._engines.get(idx)
+        if eng is None:
+            eng = _Engine(self.config, device)
+            self._engines[idx] = eng
+        from .frontend import frontend_tables
+        fb, win = frontend_tables(self.config.mel_bins)
+        eng.sync_weights(self.state_dict(), {"frontend.mel_filterbank": fb, "frontend.window": win})
+        return eng
+
+    def _check_input(self, x: torch.Tensor, what: str) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor):
+            raise TypeError(f"{what} must be a torch.Tensor")
+        dev = self._device()
+        if x.device != dev and not (x.device.type == "cuda" and dev.type == "cuda" and
+                                    (x.device.index or 0) == (dev.index or 0)):
+            raise RuntimeError(f"{what} is on {x.device} but the model is on {dev}")
+        return x.to(torch.float32).contiguous()
+
+    # ---- reference API ----------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, mel_spectrogram: torch.Tensor, return_features: bool = False
+                ) -> Union[torch.Tensor, Tuple[torch.Tensor, Dict[str, torch.Tensor]]]:
+        """(B, T, mel_bins) -> logits (B, (T+1)//2, vocab) [, features].  model.py:333-368"""
+        mel = self._check_input(mel_spectrogram, "mel_spectrogram")
+        if mel.dim() != 3 or mel.size(2) != self.config.mel_bins:
+            raise RuntimeError(f"expected (batch, frames, {self.config.mel_bins}) input, got {tuple(mel.shape)}")
+        eng = self._engine(mel.device)
+        B, T, _ = mel.shape
+        L = self.get_output_length(T)
+        logits = torch.empty(B, L, self.config.vocab_size, device=mel.device, dtype=torch.float32)
+        feats = None
+        if return_features:
+            feats = {k: torch.empty(B, L, self.config.d_model, device=mel.device, dtype=torch.float32)
+                     for k in ("temporal_binding", "local_features", "fused_features")}
+        if B > 0 and T > 0:
+            _native.check(eng.lib.vasr_forward(
+                eng.handle, _native.ptr(mel), B, T, _native.ptr(logits),
+                _native.ptr(feats["temporal_binding"]) if feats else None,
+                _native.ptr(feats["local_features"]) if feats else None,
+                _native.ptr(feats["fused_features"]) if feats else None, _stream_ptr(mel.device)))
+        return (logits, feats) if return_features else logits
+
+    def get_output_length(self, input_length: int) -> int:
+        """model.py:370-383"""
+        return (input_length + 1) // 2
+
+    @torch.no_grad()
+    def transcribe(self, audio: torch.Tensor) -> List[List[int]]:
+        """Fused fast path: 16 kHz PCM (S,) | (B, S) -> greedy CTC token ids per utterance
+        (compute_mel_spectrogram -> forward -> ctc_greedy_decode, scripts/transcribe.py:69-82).
+        A CUDA tensor is consumed in place; a CPU tensor is copied host->device inside the call
+        (pin it for full PCIe speed) and only the token ids come back."""
+        if audio.dim() == 1:
+            audio = audio.unsqueeze(0)
+        B, S = audio.shape
+        dev = self._device()
+        eng = self._engine(dev)
+        L = self.get_output_length(1 + S // 160)
+        if audio.device.type == "cpu":
+            pcm = audio.to(torch.float32).contiguous()
+            tokens = torch.empty(B, L, dtype=torch.int32, pin_memory=True)
+            lens = torch.empty(B, dtype=torch.int32, pin_memory=True)
+            _native.check(eng.lib.vasr_transcribe_host(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
+                                                       _native.ptr(lens)))
+        else:
+            pcm = self._check_input(audio, "audio")
+            tokens = torch.empty(B, L, dtype=torch.int32, device=pcm.device)
+            lens = torch.empty(B, dtype=torch.int32, device=pcm.device)
+            _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
+                                                  _native.ptr(lens), _stream_ptr(pcm.device)))
+            tokens, lens = tokens.cpu(), lens.cpu()
+        return [tokens[b, : int(lens[b])].tolist() for b in range(B)]
+
+    def extend_positional_table(self, rows: int) -> None:
+        """Regenerate pe_time with `rows` rows by the formula of model.py:94-100.  The reference
+        stops at 5000 tokens (~100 s) and raises beyond; long-form input needs a longer table."""
+        pos = self.temporal_binding.pos_encoding
+        pos.pe_time = time_table(rows, self.config.d_model).to(pos.pe_time.device)
+
+    @classmethod
+    def from_pretrained(cls, model_name_or_path: str, quantized: bool = False, **kwargs) -> "VELOCITYASR":
+        """model.py:385-433: local checkpoint with keys 'config' and 'model_state_dict' (or a bare
+        state dict).  Hub names are not implemented in the reference either."""
+        if not os.path.exists(model_name_or_path):
+            raise NotImplementedError(
+                "Model hub download not yet implemented. Please provide a local path to the checkpoint.")
+        ckpt = torch.load(model_name_or_path, map_location="cpu")
+        cfg = VelocityASRConfig.from_dict(ckpt["config"]) if "config" in ckpt else VelocityASRConfig()
+        model = cls(cfg)
+        sd = ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt
+        rows = sd["temporal_binding.pos_encoding.pe_time"].shape[0]
+        if rows != 5000:
+            model.extend_positional_table(rows)
+        model.load_state_dict(sd)
+        return model
+
+    def save_pretrained(self, save_path: str):
+        """model.py:435-467"""
+        os.makedirs(os.path.dirname(save_path) or ".", exist_ok=True)
+        torch.save({"config": self.config.to_dict(), "model_state_dict": self.state_dict()}, save_path)
+
+    def count_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    # ---- module-level seams for parity tests (reference classes SSMBlock, HierarchicalGlobalContext,
+    # CTCOutputHead) ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_ssm_block(self, x: torch.Tensor, layer: int, stack: str = "local", scan_mode: Optional[str] = None):
+        x = self._check_input(x, "x")
+        eng = self._engine(x.device)
+        out = torch.empty_like(x)
+        mode = -1 if scan_mode is None else _native.SCAN_MODE_ID[scan_mode]
+        _native.check(eng.lib.vasr_ssm_block(eng.handle, 0 if stack == "local" else 1, layer, mode, _native.ptr(x),
+                                             x.size(0), x.size(1), _native.ptr(out), _stream_ptr(x.device)))
+        return out
+
+    @torch.no_grad()
+    def run_global_context(self, local_features: torch.Tensor):
+        x = self._check_input(local_features, "local_features")
+        eng = self._engine(x.device)
+        out = torch.empty_like(x)
+        _native.check(eng.lib.vasr_global_context(eng.handle, _native.ptr(x), x.size(0), x.size(1), _native.ptr(out),
+                                                  _stream_ptr(x.device)))
+        return out
+
+    @torch.no_grad()
+    def run_ctc_head(self, x: torch.Tensor):
+        x = self._check_input(x, "x")
+        eng = self._engine(x.device)
+        out = torch.empty(x.size(0), x.size(1), self.config.vocab_size, device=x.device, dtype=torch.float32)
+        _native.check(eng.lib.vasr_ctc_head(eng.handle, _native.ptr(x), x.size(0), x.size(1), _native.ptr(out),
+                                            _stream_ptr(x.device)))
+        return out
