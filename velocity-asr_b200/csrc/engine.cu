@@ -134,10 +134,12 @@ struct Work {
   float *ga, *gb, *g2, *g2n, *kv;
   float* logits;
   int32_t* pred;
+  float* pcm_stage;      // device copies for the *_host entry points
+  int32_t *tok_stage, *len_stage;
 };
 
 // Carves the arena; with measure_only it just computes the size.
-size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w) {
+size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w, bool need_stage = false) {
   Arena a = h->ws;
   a.reset();
   Work t{};
@@ -171,12 +173,18 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   t.kv = a.take<float>(q.M2 * 2 * q.att);
   if (need_logits) t.logits = a.take<float>(q.M * q.V);
   t.pred = a.take<int32_t>(q.M);
+  if (need_stage) {
+    t.pcm_stage = a.take<float>(q.B * q.S);
+    t.tok_stage = a.take<int32_t>(q.M);
+    t.len_stage = a.take<int32_t>(q.B);
+  }
   if (w) *w = t;
   return a.used + 256;
 }
 
-int ensure_workspace(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w) {
-  const size_t need = carve(h, q, need_mel, need_logits, nullptr);
+int ensure_workspace(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Work* w,
+                     bool need_stage = false) {
+  const size_t need = carve(h, q, need_mel, need_logits, nullptr, need_stage);
   if (need > h->ws.bytes) {
     CK(cudaDeviceSynchronize());
     if (h->ws.base) CK(cudaFree(h->ws.base));
@@ -187,7 +195,7 @@ int ensure_workspace(vasr_handle* h, const Dims& q, bool need_mel, bool need_log
     h->ws.base = static_cast<char*>(p);
     h->ws.bytes = need;
   }
-  carve(h, q, need_mel, need_logits, w);
+  carve(h, q, need_mel, need_logits, w, need_stage);
   return VASR_OK;
 }
 
@@ -478,6 +486,7 @@ int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int 
   g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
   g.W = h->dft_w; g.C = k.spec; g.ldc = SPEC_LD;
   g.M = q.B * q.T; g.N = 2 * N_FREQ; g.K = N_FFT;
+  g.blocked_sum = 1;
   KL(launch_gemm(g, s, &h->launches));
   KL(launch_mel_log(k.spec, SPEC_LD, k.raw, q.B * q.T, N_FREQ, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, s,
                     &h->launches));
@@ -788,16 +797,19 @@ int vasr_ctc_greedy(const float* logits_dev, int64_t B, int64_t L, int64_t V, in
   return VASR_OK;
 }
 
-int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int32_t* tokens_dev,
-                    int32_t* lens_dev, void* stream) {
-  RET(check_ready(h));
-  if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev) return fail(VASR_ERR_INVALID, "null argument");
-  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pcm_host, int64_t B, int64_t S,
+                           int32_t* tokens_dev, int32_t* lens_dev, int32_t* tokens_host, int32_t* lens_host,
+                           cudaStream_t s) {
+  const bool host = pcm_host != nullptr;
   const Dims q = make_dims(h, B, S, vasr_num_frames(S));
   Work k;
-  RET(ensure_workspace(h, q, true, true, &k));
+  RET(ensure_workspace(h, q, true, true, &k, host));
+  if (host) {
+    CK(cudaMemcpyAsync(k.pcm_stage, pcm_host, (size_t)B * S * sizeof(float), cudaMemcpyHostToDevice, s));
+    pcm_dev = k.pcm_stage;
+    tokens_dev = k.tok_stage;
+    lens_dev = k.len_stage;
+  }
   timing_begin(h, s);
   RET(run_mel(h, q, k, pcm_dev, 1, s));
   KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches));
@@ -805,32 +817,31 @@ int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, 
   KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));
   KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches));
   timing_end(h, s);
+  if (host) {
+    CK(cudaMemcpyAsync(tokens_host, tokens_dev, (size_t)q.M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(lens_host, lens_dev, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   return VASR_OK;
+}
+
+int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int32_t* tokens_dev,
+                    int32_t* lens_dev, void* stream) {
+  RET(check_ready(h));
+  if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev) return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
+  RET(bind_device(h));
+  return transcribe_impl(h, pcm_dev, nullptr, B, S, tokens_dev, lens_dev, nullptr, nullptr,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64_t S, int32_t* tokens_host,
                          int32_t* lens_host) {
   RET(check_ready(h));
   if (B <= 0 || !pcm_host || !tokens_host || !lens_host) return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
   RET(bind_device(h));
-  const int64_t L = vasr_num_tokens(vasr_num_frames(S));
-  cudaStream_t s = h->own_stream;
-  float* pcm = nullptr;
-  int32_t *tok = nullptr, *len = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&pcm), (size_t)B * S * sizeof(float), s));
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&tok), (size_t)B * L * sizeof(int32_t), s));
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&len), (size_t)B * sizeof(int32_t), s));
-  CK(cudaMemcpyAsync(pcm, pcm_host, (size_t)B * S * sizeof(float), cudaMemcpyHostToDevice, s));
-  int r = vasr_transcribe(h, pcm, B, S, tok, len, s);
-  if (r == VASR_OK) {
-    CK(cudaMemcpyAsync(tokens_host, tok, (size_t)B * L * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(lens_host, len, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  }
-  cudaFreeAsync(pcm, s);
-  cudaFreeAsync(tok, s);
-  cudaFreeAsync(len, s);
-  CK(cudaStreamSynchronize(s));
-  return r;
+  return transcribe_impl(h, nullptr, pcm_host, B, S, nullptr, nullptr, tokens_host, lens_host, h->own_stream);
 }
 
 int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev, float* out_dev,

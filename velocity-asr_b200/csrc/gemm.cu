@@ -18,7 +18,11 @@ constexpr int LDT = BK + 2;  // 18-float rows: 8-byte LDS of 16 rows hit 32 dist
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-__global__ void __launch_bounds__(256, 2) gemm_tn_kernel(GemmArgs g) {
+// BLOCKED: every 16-wide k tile is summed into fresh registers and then added to the running
+// total (two-level summation).  Used for the 400-term DFT rows, where plain running sums lose
+// ~sqrt(K) ulps and the log of a weak mel bin amplifies it past the 1e-4 mel tolerance.
+template <bool BLOCKED>
+__global__ void __launch_bounds__(256, BLOCKED ? 1 : 2) gemm_tn_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[2][BM * LDT];
   __shared__ __align__(16) float Bs[2][BN * LDT];
 
@@ -73,10 +77,14 @@ __global__ void __launch_bounds__(256, 2) gemm_tn_kernel(GemmArgs g) {
   };
 
   u64 acc[8][4];
+  u64 tot[BLOCKED ? 8 : 1][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j] = 0ull;
+      if (BLOCKED) tot[i][j] = 0ull;
+    }
 
   const int nk = K / BK;
   gload(0);
@@ -99,9 +107,24 @@ __global__ void __launch_bounds__(256, 2) gemm_tn_kernel(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma2(a[i], b[j], acc[i][j]);
     }
+    if (BLOCKED) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tot[i][j] = add2(tot[i][j], acc[i][j]);
+          acc[i][j] = 0ull;
+        }
+    }
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
     buf ^= 1;
+  }
+  if (BLOCKED) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
   }
 
   // ---- epilogue
@@ -159,7 +182,8 @@ cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches) {
     return cudaErrorInvalidValue;
   const int64_t tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  gemm_tn_kernel<<<(unsigned)tiles, 256, 0, s>>>(g);
+  if (g.blocked_sum) gemm_tn_kernel<true><<<(unsigned)tiles, 256, 0, s>>>(g);
+  else gemm_tn_kernel<false><<<(unsigned)tiles, 256, 0, s>>>(g);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -30,6 +30,7 @@ struct GemmArgs {
   const float* pe_freq = nullptr;  // (N - pe_half)
   int pe_half = 0;
   int64_t pe_rows = 0;
+  int blocked_sum = 0;             // two-level summation over k tiles (used by the DFT rows)
 };
 cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches);
 
