@@ -132,10 +132,16 @@ int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64
 int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev,
                 float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream);
 
+/* Same contract through the tensor-core kernel (tcgen05 + TMEM + TMA, 3xTF32 split): the
+ * kernel every token-sized projection of the model runs on.  K % 4 == 0. */
+int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev,
+                   float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream);
+
 /* ---- bookkeeping for the bench: kernels launched by this handle since creation, and the
  * share of the last vasr_transcribe spent in the scan (device ms, CUDA events on `stream`)
  * when timing is enabled with vasr_set_timing(h, 1). */
 int64_t vasr_kernel_launches(const vasr_handle* h);
+int64_t vasr_tc_launches(const vasr_handle* h);   /* of which: tensor-core projection launches */
 int vasr_set_timing(vasr_handle* h, int enabled);
 int vasr_last_timing(const vasr_handle* h, float* scan_ms, int32_t* scan_launches, float* total_ms);
 int64_t vasr_workspace_bytes(const vasr_handle* h);

@@ -61,6 +61,35 @@ def test_linear(va, M, K, N, act):
     assert rel(y2, O.linear(x.double().numpy(), w.double().numpy())) < 2e-6
 
 
+@pytest.mark.parametrize("M,K,N,act", [(128, 32, 128, None), (1000, 192, 768, None), (5000, 384, 512, "softplus"),
+                                       (700, 48, 192, None), (513, 240, 192, "gelu"), (130, 192, 1000, None),
+                                       (3000, 384, 192, "sigmoid"), (48064, 192, 384, "gelu")])
+def test_linear_tensor_cores(va, M, K, N, act):
+    """tcgen05 / TMEM / TMA projection kernel with the 3xTF32 split: fp32-grade accuracy."""
+    g = torch.Generator().manual_seed(M + 3 * N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    y = va.linear(x.cuda(), w.cuda(), b.cuda(), activation=act, tensor_cores=True)
+    ref = O.linear(x.double().numpy(), w.double().numpy(), b.double().numpy())
+    ref = {None: lambda v: v, "gelu": O.gelu, "softplus": O.softplus, "sigmoid": O.sigmoid}[act](ref)
+    assert y.shape == (M, N)
+    assert rel(y, ref) < 5e-6
+    y_simt = va.linear(x.cuda(), w.cuda(), b.cuda(), activation=act) if K % 16 == 0 else None
+    if y_simt is not None:
+        assert rel(y, y_simt.double().cpu().numpy()) < 5e-6
+
+
+def test_model_runs_on_tensor_cores(va, golden):
+    """The token-sized projections of a forward pass go through the tcgen05 kernel."""
+    from velocity_asr import _native
+    m = make_model(va, "sequential")
+    mel = torch.randn(4, 401, 80, device="cuda")
+    m(mel)
+    eng = m._engine(mel.device)
+    assert _native.lib().vasr_tc_launches(eng.handle) >= 8 * 5
+
+
 # ------------------------------------------------------------------ front end ------------
 def test_log_mel_golden(va, golden):
     g = golden("frontend")

@@ -4,6 +4,7 @@
 // (scripts/transcribe.py:69-82 -> audio.py:65 -> model.py:333-368 -> decode.py:27).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -85,6 +86,11 @@ struct vasr_handle {
   int *fb_lo = nullptr, *fb_off = nullptr;
   float* fb_w = nullptr;
 
+  std::unordered_map<const float*, std::pair<float*, float*>> split;   // W -> (W_hi, W_lo)
+  int num_sms = 148;
+  int use_tc = 1;          // VASR_GEMM=simt forces the CUDA-core projection kernel
+  int64_t tc_launches = 0;
+
   Arena ws;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
@@ -118,8 +124,8 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
   q.K2 = k2 < q.K1 ? k2 : q.K1;
   q.Mg = B * q.K1;
   q.M2 = B * q.K2;
-  q.Tp = T + 2;
-  q.ldp = ((S + 2 * PAD + 3) / 4) * 4;
+  q.Tp = T + 2 + ((T + 2) & 1);                       // even: batch stride is a multiple of the 2-frame row stride
+  q.ldp = ((S + 2 * PAD + HOP - 1) / HOP) * HOP;      // multiple of the hop: same for the STFT frame view
   q.d = h->cfg.d_model;
   q.di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
   q.n_mels = h->cfg.mel_bins;
@@ -353,6 +359,14 @@ void free_weights(vasr_handle* h) {
   h->weight_allocs.clear();
   h->local.clear();
   h->global.clear();
+  {
+    auto keep = h->split.find(h->dft_w);
+    std::pair<float*, float*> dft;
+    const bool has = keep != h->split.end();
+    if (has) dft = keep->second;
+    h->split.clear();
+    if (has) h->split[h->dft_w] = dft;
+  }
   h->committed = false;
 }
 
@@ -365,13 +379,41 @@ void free_weights(vasr_handle* h) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
   } while (0)
 
+// one projection: tensor cores for the token-sized ones, CUDA cores for the few-row ones
+int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
+  auto it = h->split.find(g.W);
+  if (h->use_tc && it != h->split.end() && g.M >= 128 && !g.blocked_sum) {
+    g.W_hi = it->second.first;
+    g.W_lo = it->second.second;
+    cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
+    if (e == cudaSuccess) {
+      ++h->tc_launches;
+      return VASR_OK;
+    }
+    if (e != cudaErrorNotSupported) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
+    (void)cudaGetLastError();
+  }
+  KL(launch_gemm(g, s, &h->launches));
+  return VASR_OK;
+}
+
 int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
            int64_t M, int64_t K, int64_t N, int act, int act_from, const float* resid, int64_t ldr,
            cudaStream_t s) {
   GemmArgs g;
   g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = act_from; g.resid = resid; g.ldr = ldr;
-  KL(launch_gemm(g, s, &h->launches));
+  return gemm(h, g, s);
+}
+
+int make_split(vasr_handle* h, const float* w, int64_t numel) {
+  float *hi = nullptr, *lo = nullptr;
+  CK(cudaMalloc(reinterpret_cast<void**>(&hi), (size_t)numel * sizeof(float)));
+  h->alloc_list->push_back(hi);
+  CK(cudaMalloc(reinterpret_cast<void**>(&lo), (size_t)numel * sizeof(float)));
+  h->alloc_list->push_back(lo);
+  KL(launch_split_tf32(w, hi, lo, numel, nullptr));
+  h->split[w] = std::make_pair(hi, lo);
   return VASR_OK;
 }
 
@@ -464,7 +506,7 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
   g.M = q.M; g.N = d; g.K = 3 * q.n_mels;
   g.act = ACT_GELU; g.act_from = 0;
   g.pe_time = h->pe_time; g.pe_freq = h->pe_freq; g.pe_half = d / 2; g.pe_rows = q.L;
-  KL(launch_gemm(g, s, &h->launches));
+  RET(gemm(h, g, s));
   KL(launch_layer_norm(k.xa, d, k.xa, d, h->tb_g, h->tb_bt, q.M, d, s, &h->launches));
   if (f_tb) CK(cudaMemcpyAsync(f_tb, k.xa, (size_t)q.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   for (size_t i = 0; i < h->local.size(); ++i)
@@ -487,7 +529,7 @@ int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int 
   g.W = h->dft_w; g.C = k.spec; g.ldc = SPEC_LD;
   g.M = q.B * q.T; g.N = 2 * N_FREQ; g.K = N_FFT;
   g.blocked_sum = 1;
-  KL(launch_gemm(g, s, &h->launches));
+  RET(gemm(h, g, s));
   KL(launch_mel_log(k.spec, SPEC_LD, k.raw, q.B * q.T, N_FREQ, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, s,
                     &h->launches));
   if (normalize) KL(launch_mel_stats(k.raw, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches));
@@ -558,6 +600,8 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   vasr_handle* h = new vasr_handle();
   h->cfg = c;
   h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if (const char* ev = getenv("VASR_GEMM")) h->use_tc = strcmp(ev, "simt") != 0;
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -681,7 +725,27 @@ int vasr_commit_weights(vasr_handle* h) {
   RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
   RET(up(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &h->w_ctc));
   RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
-  (void)di;
+  {
+    const int64_t V = c.vocab_size;
+    RET(make_split(h, h->tb_w, (int64_t)d * 3 * nm));
+    for (auto* st : {&h->local, &h->global})
+      for (BlockW& w : *st) {
+        RET(make_split(h, w.w_in, (int64_t)2 * di * d));
+        RET(make_split(h, w.w_xdt, (int64_t)(2 * w.N + di) * di));
+        RET(make_split(h, w.w_out, (int64_t)d * di));
+        RET(make_split(h, w.w_f1, (int64_t)di * d));
+        RET(make_split(h, w.w_f2, (int64_t)d * di));
+      }
+    RET(make_split(h, h->p1_w, (int64_t)d * d));
+    RET(make_split(h, h->p2_w, (int64_t)d * d));
+    RET(make_split(h, h->w_q, (int64_t)att * d));
+    RET(make_split(h, h->w_kv, (int64_t)2 * att * d));
+    RET(make_split(h, h->w_o, (int64_t)d * att));
+    RET(make_split(h, h->w_f3, (int64_t)3 * d * 2 * d));
+    RET(make_split(h, h->w_fo, (int64_t)d * d));
+    RET(make_split(h, h->w_ctc, V * d));
+    CK(cudaDeviceSynchronize());
+  }
   h->committed = true;
   return VASR_OK;
 }
@@ -855,6 +919,30 @@ int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float
   return VASR_OK;
 }
 
+int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev, float* out_dev,
+                   int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream) {
+  if (!x_dev || !w_dev || !out_dev) return fail(VASR_ERR_INVALID, "null argument");
+  if (act < 0 || act > 3) return fail(VASR_ERR_INVALID, "unknown activation");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float *hi = nullptr, *lo = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&hi), (size_t)N * K * sizeof(float), s));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&lo), (size_t)N * K * sizeof(float), s));
+  KL(launch_split_tf32(w_dev, hi, lo, N * K, s));
+  GemmArgs g;
+  g.A = x_dev; g.lda = ldx; g.W = w_dev; g.W_hi = hi; g.W_lo = lo; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
+  cudaError_t e = launch_gemm_tc(g, sms, s, nullptr);
+  cudaFreeAsync(hi, s);
+  cudaFreeAsync(lo, s);
+  if (e == cudaErrorNotSupported) return fail(VASR_ERR_UNSUPPORTED, "tensor map could not be encoded for this view");
+  if (e != cudaSuccess) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
+  return VASR_OK;
+}
+
+int64_t vasr_tc_launches(const vasr_handle* h) { return h ? h->tc_launches : 0; }
 int64_t vasr_kernel_launches(const vasr_handle* h) { return h ? h->launches : 0; }
 int64_t vasr_workspace_bytes(const vasr_handle* h) { return h ? (int64_t)h->ws.bytes : 0; }
 

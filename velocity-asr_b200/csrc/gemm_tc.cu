@@ -1,0 +1,412 @@
+// gemm_tc.cu — tensor-core projection kernel for sm_100a: C = epi(A · Wᵀ) with fp32-grade accuracy.
+//
+// tcgen05.mma (kind::tf32) issued by one thread, operands staged in shared memory by TMA
+// (128-byte swizzle), accumulators in TMEM, read back with tcgen05.ld for a fused epilogue.
+//
+// Accuracy.  One TF32 pass carries ~1e-3 relative error, which flips ~0.3 % of the CTC argmaxes
+// (SURVEY.md section 7.3c).  Each fp32 operand is therefore split exactly into hi + lo, both
+// representable in TF32 (hi = top 19 bits, lo = top 19 bits of the remainder), and every k-step
+// issues three MMAs, A_hi·W_hi + A_lo·W_hi + A_hi·W_lo, accumulated in fp32 in TMEM (error
+// ~2^-21 per product).  W is split once at weight load; A is split in shared memory by four
+// converter warps between the TMA arrival and the MMA issue (in place for hi, a second buffer
+// for lo), so activations never carry a second copy through HBM.
+//
+// Structure (persistent, one CTA per SM, 10 warps):
+//   warp 0      TMA producer      : A tile (128 x 32 fp32) + W_hi/W_lo tiles (128 x 32) per stage
+//   warp 1      MMA issuer        : 12 tcgen05.mma per stage; tcgen05.commit frees the stage
+//   warps 2-5   converters        : hi/lo split of the A tile, fence.proxy.async, arrive
+//   warps 6-9   epilogue          : TMEM -> registers -> smem transpose -> coalesced global store
+// Two TMEM accumulators (2 x 128 columns) let the epilogue of tile i overlap the mainloop of
+// tile i+1.  Rows of A may come from a strided / overlapping batched view (conv and STFT frames),
+// addressed with a 3-D tensor map (k, row-in-batch, batch); M tiles never straddle a batch.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vasr {
+
+namespace {
+
+constexpr int TBM = 128, TBN = 128, TBK = 32, STAGES = 3;
+constexpr int TILE_BYTES = TBM * TBK * 4;            // 16 KB (A and W tiles are the same size)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi | A_lo | W_hi | W_lo
+constexpr int EPI_LD = 33;
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // per-warp 32 x 33 transpose buffers
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + align slack
+constexpr int TC_THREADS = 320;
+constexpr uint32_t TMEM_COLS = 256;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
+// K-major A and B, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TBN >> 3) << 17) | ((TBM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte swizzle, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+  int64_t M, N, K;
+  int64_t rows_per_batch;     // rows of A per batch (== M for a plain matrix)
+  int64_t n_batches;
+  int m_tiles_per_batch;
+  int n_tiles;
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int act, act_from;
+  const float* resid;
+  int64_t ldr;
+  const float* pe_time;
+  const float* pe_freq;
+  int pe_half;
+  int64_t pe_rows;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+               const __grid_constant__ CUtensorMap tmWlo, const TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  // barrier map: full[s] = 0..2, conv[s] = 3..5, empty[s] = 6..8, tfull[a] = 9..10, tempty[a] = 11..12
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t stage0 = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(BAR(s), 1);          // full: producer's expect_tx arrive
+      mbar_init(BAR(3 + s), 128);    // conv: every converter thread
+      mbar_init(BAR(6 + s), 1);      // empty: tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(BAR(9 + a), 1);      // tmem full: tcgen05.commit
+      mbar_init(BAR(11 + a), 128);   // tmem empty: every epilogue thread
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = (int)((g.K + TBK - 1) / TBK);
+  const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % g.n_tiles);
+        const int64_t mt = tile / g.n_tiles;
+        const int batch = (int)(mt / g.m_tiles_per_batch);
+        const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(BAR(6 + stage), phase ^ 1);
+          const uint32_t sb = stage0 + stage * STAGE_BYTES;
+          mbar_expect_tx(BAR(stage), 3 * TILE_BYTES);
+          tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(stage));
+          tma_load_2d(sb + 2 * TILE_BYTES, &tmWhi, kb * TBK, nt * TBN, BAR(stage));
+          tma_load_2d(sb + 3 * TILE_BYTES, &tmWlo, kb * TBK, nt * TBN, BAR(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t stage = 0, phase = 0;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = (uint32_t)(it & 1);
+      mbar_wait(BAR(11 + acc), (uint32_t)((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * TBN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(BAR(3 + stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sb = stage0 + stage * STAGE_BYTES;
+          const uint64_t da_hi = umma_desc(sb), da_lo = umma_desc(sb + TILE_BYTES);
+          const uint64_t db_hi = umma_desc(sb + 2 * TILE_BYTES), db_lo = umma_desc(sb + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < TBK / 8; ++k4) {
+            const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
+            umma_tf32(tmem_d, da_lo + adv, db_hi + adv, (kb | k4) != 0);
+            umma_tf32(tmem_d, da_hi + adv, db_lo + adv, 1);
+            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, 1);
+          }
+          umma_commit(BAR(6 + stage));
+          if (kb == nkb - 1) umma_commit(BAR(9 + acc));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converters: exact hi/lo split of the A tile =====================
+    const int ct = threadIdx.x - 64;   // 0..127
+    uint32_t stage = 0, phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(BAR(stage), phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          const int idx = ct + 128 * i;
+          float4 v = hi[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(BAR(3 + stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may read
+    float* cs = epi + q * 32 * EPI_LD;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = (int)(tile % g.n_tiles);
+      const int64_t mt = tile / g.n_tiles;
+      const int64_t batch = mt / g.m_tiles_per_batch;
+      const int64_t mi0 = (mt % g.m_tiles_per_batch) * TBM;
+      const uint32_t acc = (uint32_t)(it & 1);
+      mbar_wait(BAR(9 + acc), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < TBN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
+        if (c == TBN / 32 - 1) {       // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(BAR(11 + acc));
+        }
+#pragma unroll
+        for (int col = 0; col < 32; ++col) cs[lane * EPI_LD + col] = __uint_as_float(v[col]);
+        __syncwarp();
+        const int64_t n = (int64_t)nt * TBN + c * 32 + lane;
+        if (n < g.N) {
+          const float bias = g.bias ? __ldg(g.bias + n) : 0.f;
+          const bool do_act = n >= g.act_from;
+          const float pef = (g.pe_time && n >= g.pe_half) ? __ldg(g.pe_freq + (n - g.pe_half)) : 0.f;
+          for (int r = 0; r < 32; ++r) {
+            const int64_t mi = mi0 + q * 32 + r;
+            if (mi >= g.rows_per_batch) break;
+            const int64_t m = batch * g.rows_per_batch + mi;
+            float x = cs[r * EPI_LD + lane] + bias;
+            if (do_act) x = apply_act(x, g.act);
+            if (g.pe_time) x += (n < g.pe_half) ? __ldg(g.pe_time + (m % g.pe_rows) * g.pe_half + n) : pef;
+            if (g.resid) x += __ldg(g.resid + m * g.ldr + n);
+            g.C[m * g.ldc + n] = x;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// exact TF32 hi/lo split of a weight matrix (done once per weight)
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                  int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  hi[i] = h;
+  lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[3], gs[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+cudaError_t launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, hi, lo, n);
+  return cudaGetLastError();
+}
+
+bool gemm_tc_supported(const GemmArgs& g) {
+  if (!encode_fn()) return false;
+  if (!g.W_hi || !g.W_lo) return false;
+  if (g.K % 4 != 0 || g.lda % 4 != 0 || g.batch_stride % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W_hi) & 15) ||
+      (reinterpret_cast<uintptr_t>(g.W_lo) & 15))
+    return false;
+  return true;
+}
+
+// Returns cudaErrorNotSupported when the tensor maps cannot be encoded (the caller then uses the
+// CUDA-core kernel); any other error is a real launch failure.
+cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64_t* launches) {
+  if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+  if (!gemm_tc_supported(g)) return cudaErrorNotSupported;
+  const int64_t rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
+  const int64_t nb = g.rows_per_batch > 0 ? g.M / g.rows_per_batch : 1;
+  if (nb * rpb != g.M) return cudaErrorNotSupported;
+  const int64_t bstride = g.rows_per_batch > 0 ? g.batch_stride : rpb * g.lda;
+
+  CUtensorMap tmA, tmWhi, tmWlo;
+  {
+    const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)rpb, (uint64_t)nb};
+    const uint64_t str[2] = {(uint64_t)g.lda * 4, (uint64_t)(bstride > 0 ? bstride : g.lda) * 4};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    if (!make_map(&tmA, g.A, 3, dims, str, box)) return cudaErrorNotSupported;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    const uint64_t str[1] = {(uint64_t)g.K * 4};
+    const uint32_t box[2] = {TBK, TBN};
+    if (!make_map(&tmWhi, g.W_hi, 2, dims, str, box)) return cudaErrorNotSupported;
+    if (!make_map(&tmWlo, g.W_lo, 2, dims, str, box)) return cudaErrorNotSupported;
+  }
+  TcArgs a;
+  a.M = g.M; a.N = g.N; a.K = g.K;
+  a.rows_per_batch = rpb;
+  a.n_batches = nb;
+  a.m_tiles_per_batch = (int)((rpb + TBM - 1) / TBM);
+  a.n_tiles = (int)((g.N + TBN - 1) / TBN);
+  a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act = g.act; a.act_from = g.act_from;
+  a.resid = g.resid; a.ldr = g.ldr;
+  a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half; a.pe_rows = g.pe_rows;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+  gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmWhi, tmWlo, a);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace vasr

@@ -40,7 +40,10 @@ _SIGNATURES = {
     "vasr_transcribe_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "vasr_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                             c_int, c_void_p]),
+    "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                       c_int, c_void_p]),
     "vasr_kernel_launches": (c_int64, [c_void_p]),
+    "vasr_tc_launches": (c_int64, [c_void_p]),
     "vasr_workspace_bytes": (c_int64, [c_void_p]),
     "vasr_set_timing": (c_int, [c_void_p, c_int]),
     "vasr_last_timing": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int32), POINTER(c_float)]),

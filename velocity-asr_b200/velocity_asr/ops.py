@@ -61,8 +61,10 @@ _ACT = {None: 0, "none": 0, "gelu": 1, "softplus": 2, "sigmoid": 3}
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-           activation: Optional[str] = None) -> torch.Tensor:
-    """F.linear (+ optional activation) on (..., K) rows; K must be a multiple of 16."""
+           activation: Optional[str] = None, tensor_cores: bool = False) -> torch.Tensor:
+    """F.linear (+ optional activation) on (..., K) rows.  tensor_cores=False: CUDA-core fp32 kernel
+    (K % 16 == 0); True: tcgen05 3xTF32 kernel (K % 4 == 0) — the one the model's token-sized
+    projections run on."""
     if x.device.type != "cuda":
         raise RuntimeError("linear runs on CUDA only (no CPU fallback)")
     x, weight, bias = map(_f32c, (x, weight, bias))
@@ -73,7 +75,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if x2.shape[0] > 0:
         lib = _native.lib()
         with torch.cuda.device(x.device):
-            _native.check(lib.vasr_linear(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(bias),
+            fn = lib.vasr_linear_tc if tensor_cores else lib.vasr_linear
+            _native.check(fn(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(bias),
                                           _native.ptr(out), N, x2.shape[0], K, N, _ACT[activation],
                                           _stream(x.device)))
     return out.reshape(*x.shape[:-1], N)
