@@ -55,7 +55,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- activations with the reference's ATen semantics --------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float softplus_t20(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+// F.softplus(beta=1, threshold=20) = x if x > 20 else log1p(exp(x)), evaluated as
+// max(x,0) + log1p(exp(-|x|)) with MUFU ex2/lg2 (series for tiny arguments): abs error ~1e-7.
+__device__ __forceinline__ float softplus_t20(float x) {
+  if (x > 20.0f) return x;
+  const float e = __expf(-fabsf(x));
+  const float l = e < 0.01f ? e * (1.0f - e * (0.5f - e * 0.33333334f)) : __logf(1.0f + e);
+  return fmaxf(x, 0.0f) + l;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SOFTPLUS = 2, ACT_SIGMOID = 3 };

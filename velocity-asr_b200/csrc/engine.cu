@@ -86,9 +86,9 @@ struct vasr_handle {
   int *fb_lo = nullptr, *fb_off = nullptr;
   float* fb_w = nullptr;
 
-  std::unordered_map<const float*, std::pair<float*, float*>> split;   // W -> (W_hi, W_lo)
   int num_sms = 148;
   int use_tc = 1;          // VASR_GEMM=simt forces the CUDA-core projection kernel
+  int dft_tc = 0;          // VASR_DFT=tc runs the windowed DFT on the tensor-core kernel too
   int64_t tc_launches = 0;
 
   Arena ws;
@@ -359,14 +359,6 @@ void free_weights(vasr_handle* h) {
   h->weight_allocs.clear();
   h->local.clear();
   h->global.clear();
-  {
-    auto keep = h->split.find(h->dft_w);
-    std::pair<float*, float*> dft;
-    const bool has = keep != h->split.end();
-    if (has) dft = keep->second;
-    h->split.clear();
-    if (has) h->split[h->dft_w] = dft;
-  }
   h->committed = false;
 }
 
@@ -381,10 +373,7 @@ void free_weights(vasr_handle* h) {
 
 // one projection: tensor cores for the token-sized ones, CUDA cores for the few-row ones
 int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
-  auto it = h->split.find(g.W);
-  if (h->use_tc && it != h->split.end() && g.M >= 128 && !g.blocked_sum) {
-    g.W_hi = it->second.first;
-    g.W_lo = it->second.second;
+  if (h->use_tc && g.M >= 128 && (!g.blocked_sum || h->dft_tc)) {
     cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
     if (e == cudaSuccess) {
       ++h->tc_launches;
@@ -406,16 +395,6 @@ int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const fl
   return gemm(h, g, s);
 }
 
-int make_split(vasr_handle* h, const float* w, int64_t numel) {
-  float *hi = nullptr, *lo = nullptr;
-  CK(cudaMalloc(reinterpret_cast<void**>(&hi), (size_t)numel * sizeof(float)));
-  h->alloc_list->push_back(hi);
-  CK(cudaMalloc(reinterpret_cast<void**>(&lo), (size_t)numel * sizeof(float)));
-  h->alloc_list->push_back(lo);
-  KL(launch_split_tf32(w, hi, lo, numel, nullptr));
-  h->split[w] = std::make_pair(hi, lo);
-  return VASR_OK;
-}
 
 int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t L, int quirk, cudaStream_t s) {
   const int di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
@@ -602,6 +581,7 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   if (const char* ev = getenv("VASR_GEMM")) h->use_tc = strcmp(ev, "simt") != 0;
+  if (const char* ev = getenv("VASR_DFT")) h->dft_tc = strcmp(ev, "tc") == 0;
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -725,27 +705,6 @@ int vasr_commit_weights(vasr_handle* h) {
   RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
   RET(up(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &h->w_ctc));
   RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
-  {
-    const int64_t V = c.vocab_size;
-    RET(make_split(h, h->tb_w, (int64_t)d * 3 * nm));
-    for (auto* st : {&h->local, &h->global})
-      for (BlockW& w : *st) {
-        RET(make_split(h, w.w_in, (int64_t)2 * di * d));
-        RET(make_split(h, w.w_xdt, (int64_t)(2 * w.N + di) * di));
-        RET(make_split(h, w.w_out, (int64_t)d * di));
-        RET(make_split(h, w.w_f1, (int64_t)di * d));
-        RET(make_split(h, w.w_f2, (int64_t)d * di));
-      }
-    RET(make_split(h, h->p1_w, (int64_t)d * d));
-    RET(make_split(h, h->p2_w, (int64_t)d * d));
-    RET(make_split(h, h->w_q, (int64_t)att * d));
-    RET(make_split(h, h->w_kv, (int64_t)2 * att * d));
-    RET(make_split(h, h->w_o, (int64_t)d * att));
-    RET(make_split(h, h->w_f3, (int64_t)3 * d * 2 * d));
-    RET(make_split(h, h->w_fo, (int64_t)d * d));
-    RET(make_split(h, h->w_ctc, V * d));
-    CK(cudaDeviceSynchronize());
-  }
   h->committed = true;
   return VASR_OK;
 }
@@ -927,16 +886,10 @@ int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const fl
   int dev = 0, sms = 148;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  float *hi = nullptr, *lo = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&hi), (size_t)N * K * sizeof(float), s));
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&lo), (size_t)N * K * sizeof(float), s));
-  KL(launch_split_tf32(w_dev, hi, lo, N * K, s));
   GemmArgs g;
-  g.A = x_dev; g.lda = ldx; g.W = w_dev; g.W_hi = hi; g.W_lo = lo; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
+  g.A = x_dev; g.lda = ldx; g.W = w_dev; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
   cudaError_t e = launch_gemm_tc(g, sms, s, nullptr);
-  cudaFreeAsync(hi, s);
-  cudaFreeAsync(lo, s);
   if (e == cudaErrorNotSupported) return fail(VASR_ERR_UNSUPPORTED, "tensor map could not be encoded for this view");
   if (e != cudaSuccess) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
   return VASR_OK;

@@ -7,15 +7,15 @@
 // (SURVEY.md section 7.3c).  Each fp32 operand is therefore split exactly into hi + lo, both
 // representable in TF32 (hi = top 19 bits, lo = top 19 bits of the remainder), and every k-step
 // issues three MMAs, A_hi·W_hi + A_lo·W_hi + A_hi·W_lo, accumulated in fp32 in TMEM (error
-// ~2^-21 per product).  W is split once at weight load; A is split in shared memory by four
-// converter warps between the TMA arrival and the MMA issue (in place for hi, a second buffer
-// for lo), so activations never carry a second copy through HBM.
+// ~2^-21 per product).  Both tiles are split in shared memory by four converter warps between the
+// TMA arrival and the MMA issue (in place for hi, a second buffer for lo), so neither activations
+// nor weights carry a second copy through HBM / L2: TMA moves 32 KB per k-step, not 64.
 //
-// Structure (persistent, one CTA per SM, 10 warps):
-//   warp 0      TMA producer      : A tile (128 x 32 fp32) + W_hi/W_lo tiles (128 x 32) per stage
+// Structure (persistent, one CTA per SM, 14 warps):
+//   warp 0      TMA producer      : A tile and W tile (128 x 32 fp32 each) per stage
 //   warp 1      MMA issuer        : 12 tcgen05.mma per stage; tcgen05.commit frees the stage
-//   warps 2-5   converters        : hi/lo split of the A tile, fence.proxy.async, arrive
-//   warps 6-9   epilogue          : TMEM -> registers -> smem transpose -> coalesced global store
+//   warps 2-5   converters        : exact hi/lo split of both tiles, fence.proxy.async, arrive
+//   warps 6-13  epilogue          : TMEM -> registers -> bias/act/pos-enc/residual -> global store
 // Two TMEM accumulators (2 x 128 columns) let the epilogue of tile i overlap the mainloop of
 // tile i+1.  Rows of A may come from a strided / overlapping batched view (conv and STFT frames),
 // addressed with a 3-D tensor map (k, row-in-batch, batch); M tiles never straddle a batch.
@@ -31,10 +31,8 @@ namespace {
 constexpr int TBM = 128, TBN = 128, TBK = 32, STAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 4;            // 16 KB (A and W tiles are the same size)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi | A_lo | W_hi | W_lo
-constexpr int EPI_LD = 33;
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;       // per-warp 32 x 33 transpose buffers
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;  // + barriers + align slack
-constexpr int TC_THREADS = 320;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+constexpr int TC_THREADS = 448;                      // 1 TMA + 1 MMA + 4 converter + 8 epilogue warps
 constexpr uint32_t TMEM_COLS = 256;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
@@ -114,6 +112,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float v) {
+  if (ACT == ACT_GELU) return gelu_erf(v);
+  if (ACT == ACT_SOFTPLUS) return softplus_t20(v);
+  if (ACT == ACT_SIGMOID) return sigmoid_f(v);
+  return v;
+}
+
 struct TcArgs {
   int64_t M, N, K;
   int64_t rows_per_batch;     // rows of A per batch (== M for a plain matrix)
@@ -132,13 +138,13 @@ struct TcArgs {
   int64_t pe_rows;
 };
 
+template <int ACT, bool PE, bool RESID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
-               const __grid_constant__ CUtensorMap tmWlo, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  // keep the pointer derived from smem_raw (no integer round trip) so accesses compile to LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   // barrier map: full[s] = 0..2, conv[s] = 3..5, empty[s] = 6..8, tfull[a] = 9..10, tempty[a] = 11..12
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
@@ -155,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(BAR(9 + a), 1);      // tmem full: tcgen05.commit
-      mbar_init(BAR(11 + a), 128);   // tmem empty: every epilogue thread
+      mbar_init(BAR(11 + a), 256);   // tmem empty: every epilogue thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,10 +190,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(BAR(6 + stage), phase ^ 1);
           const uint32_t sb = stage0 + stage * STAGE_BYTES;
-          mbar_expect_tx(BAR(stage), 3 * TILE_BYTES);
+          mbar_expect_tx(BAR(stage), 2 * TILE_BYTES);
           tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(stage));
-          tma_load_2d(sb + 2 * TILE_BYTES, &tmWhi, kb * TBK, nt * TBN, BAR(stage));
-          tma_load_2d(sb + 3 * TILE_BYTES, &tmWlo, kb * TBK, nt * TBN, BAR(stage));
+          tma_load_2d(sb + 2 * TILE_BYTES, &tmW, kb * TBK, nt * TBN, BAR(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -229,19 +234,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(stage), phase);
-        float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + TILE_BYTES);
 #pragma unroll
-        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-          const int idx = ct + 128 * i;
-          float4 v = hi[idx];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-          hi[idx] = h;
-          lo[idx] = l;
+        for (int tile2 = 0; tile2 < 2; ++tile2) {       // 0: A (hi at +0, lo at +1), 1: W (hi at +2, lo at +3)
+          float4* __restrict__ hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + 2 * tile2 * TILE_BYTES);
+          float4* __restrict__ lo = hi + TILE_BYTES / 16;
+          float4 v[TILE_BYTES / 16 / 128];
+#pragma unroll
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) v[i] = hi[ct + 128 * i];
+#pragma unroll
+          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
+            hi[ct + 128 * i] = h;
+            lo[ct + 128 * i] = l;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(BAR(3 + stage));
@@ -250,45 +259,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
+    // A thread owns one output row (TMEM lane = row): it reads 32 accumulator columns at a time and
+    // writes its own 128-byte row segment as eight 16-byte stores.  ACT / PE / RESID are template
+    // parameters, so the loops below carry no per-element branches.
     const int q = warp & 3;                         // TMEM lane quadrant this warp may read
-    float* cs = epi + q * 32 * EPI_LD;
+    const int chalf = (warp - 6) >> 2;              // which two of the four 32-column chunks
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = (int)(tile % g.n_tiles);
       const int64_t mt = tile / g.n_tiles;
       const int64_t batch = mt / g.m_tiles_per_batch;
-      const int64_t mi0 = (mt % g.m_tiles_per_batch) * TBM;
+      const int64_t mi = (mt % g.m_tiles_per_batch) * TBM + q * 32 + lane;   // row within the batch
+      const bool row_ok = mi < g.rows_per_batch;
+      const int64_t m = batch * g.rows_per_batch + mi;
+      const int64_t ncol0 = (int64_t)nt * TBN;
+      float* crow = g.C + m * g.ldc + ncol0;
+      const float* rrow = RESID ? g.resid + m * g.ldr + ncol0 : nullptr;
+      const float* prow = PE ? g.pe_time + mi * g.pe_half : nullptr;
       const uint32_t acc = (uint32_t)(it & 1);
       mbar_wait(BAR(9 + acc), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
+      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
-        if (c == TBN / 32 - 1) {       // accumulator fully read: hand it back to the MMA warp
+        if (c == 2 * chalf + 1) {      // this warp's share of the accumulator is read: hand it back
           tc_fence_before();
           mbar_arrive(BAR(11 + acc));
         }
+        if (!row_ok) continue;
 #pragma unroll
-        for (int col = 0; col < 32; ++col) cs[lane * EPI_LD + col] = __uint_as_float(v[col]);
-        __syncwarp();
-        const int64_t n = (int64_t)nt * TBN + c * 32 + lane;
-        if (n < g.N) {
-          const float bias = g.bias ? __ldg(g.bias + n) : 0.f;
-          const bool do_act = n >= g.act_from;
-          const float pef = (g.pe_time && n >= g.pe_half) ? __ldg(g.pe_freq + (n - g.pe_half)) : 0.f;
-          for (int r = 0; r < 32; ++r) {
-            const int64_t mi = mi0 + q * 32 + r;
-            if (mi >= g.rows_per_batch) break;
-            const int64_t m = batch * g.rows_per_batch + mi;
-            float x = cs[r * EPI_LD + lane] + bias;
-            if (do_act) x = apply_act(x, g.act);
-            if (g.pe_time) x += (n < g.pe_half) ? __ldg(g.pe_time + (m % g.pe_rows) * g.pe_half + n) : pef;
-            if (g.resid) x += __ldg(g.resid + m * g.ldr + n);
-            g.C[m * g.ldc + n] = x;
+        for (int k = 0; k < 8; ++k) {
+          const int64_t n = ncol0 + c * 32 + 4 * k;
+          if (n >= g.N) break;        // N % 4 == 0: a group of four columns is valid or not as a whole
+          float4 x = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                 __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
+          if (g.bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
           }
+          if (ACT != ACT_NONE && n >= g.act_from) {
+            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
+            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+          }
+          if (PE) {
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(n < g.pe_half ? prow + n : g.pe_freq + (n - g.pe_half)));
+            x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
+          }
+          if (RESID) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + c * 32 + 4 * k));
+            x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+          }
+          *reinterpret_cast<float4*>(crow + c * 32 + 4 * k) = x;
         }
-        __syncwarp();
       }
     }
   }
@@ -299,17 +322,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
-}
-
-// exact TF32 hi/lo split of a weight matrix (done once per weight)
-__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
-                                  int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const float v = w[i];
-  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  hi[i] = h;
-  lo[i] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -346,19 +358,16 @@ bool make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dim
 
 }  // namespace
 
-cudaError_t launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
-  if (n <= 0) return cudaSuccess;
-  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, hi, lo, n);
-  return cudaGetLastError();
-}
-
 bool gemm_tc_supported(const GemmArgs& g) {
   if (!encode_fn()) return false;
-  if (!g.W_hi || !g.W_lo) return false;
   if (g.K % 4 != 0 || g.lda % 4 != 0 || g.batch_stride % 4 != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W_hi) & 15) ||
-      (reinterpret_cast<uintptr_t>(g.W_lo) & 15))
-    return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
+  // the epilogue moves 16-byte groups of four columns
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((g.N & 3) || (g.ldc & 3) || !al16(g.C) || (g.act_from & 3)) return false;
+  if (g.bias && !al16(g.bias)) return false;
+  if (g.resid && ((g.ldr & 3) || !al16(g.resid))) return false;
+  if (g.pe_time && ((g.pe_half & 3) || !al16(g.pe_time) || !al16(g.pe_freq))) return false;
   return true;
 }
 
@@ -370,9 +379,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   const int64_t rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
   const int64_t nb = g.rows_per_batch > 0 ? g.M / g.rows_per_batch : 1;
   if (nb * rpb != g.M) return cudaErrorNotSupported;
+  if (g.pe_time && g.pe_rows != rpb) return cudaErrorNotSupported;   // pos-enc row == row within the batch
   const int64_t bstride = g.rows_per_batch > 0 ? g.batch_stride : rpb * g.lda;
 
-  CUtensorMap tmA, tmWhi, tmWlo;
+  CUtensorMap tmA, tmW;
   {
     const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)rpb, (uint64_t)nb};
     const uint64_t str[2] = {(uint64_t)g.lda * 4, (uint64_t)(bstride > 0 ? bstride : g.lda) * 4};
@@ -383,8 +393,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.K * 4};
     const uint32_t box[2] = {TBK, TBN};
-    if (!make_map(&tmWhi, g.W_hi, 2, dims, str, box)) return cudaErrorNotSupported;
-    if (!make_map(&tmWlo, g.W_lo, 2, dims, str, box)) return cudaErrorNotSupported;
+    if (!make_map(&tmW, g.W, 2, dims, str, box)) return cudaErrorNotSupported;
   }
   TcArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K;
@@ -396,15 +405,27 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half; a.pe_rows = g.pe_rows;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmWhi, tmWlo, a);
+  const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;
+  cudaError_t err = cudaSuccess;
+  auto go = [&](auto kernel) {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmW, a);
+  };
+#define VASR_TC_CASE(ACTV)                                                  \
+  if (g.act == ACTV) {                                                      \
+    if (pe && rs) go(gemm_tc_kernel<ACTV, true, true>);                     \
+    else if (pe) go(gemm_tc_kernel<ACTV, true, false>);                     \
+    else if (rs) go(gemm_tc_kernel<ACTV, false, true>);                     \
+    else go(gemm_tc_kernel<ACTV, false, false>);                            \
+  }
+  VASR_TC_CASE(ACT_NONE)
+  VASR_TC_CASE(ACT_GELU)
+  VASR_TC_CASE(ACT_SOFTPLUS)
+  VASR_TC_CASE(ACT_SIGMOID)
+#undef VASR_TC_CASE
+  if (err != cudaSuccess) return err;
   if (launches) ++*launches;
   return cudaGetLastError();
 }

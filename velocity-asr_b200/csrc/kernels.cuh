@@ -31,14 +31,11 @@ struct GemmArgs {
   int pe_half = 0;
   int64_t pe_rows = 0;
   int blocked_sum = 0;             // two-level summation over k tiles (used by the DFT rows)
-  const float* W_hi = nullptr;     // exact TF32 split of W (tensor-core path); NULL -> CUDA-core path only
-  const float* W_lo = nullptr;
 };
 cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches);
 // tcgen05 / TMEM / TMA path with 3xTF32 split accumulation (gemm_tc.cu).  Returns
 // cudaErrorNotSupported when a tensor map cannot be encoded for this view.
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64_t* launches);
-cudaError_t launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s);
 
 // ---------------------------------------------------------------- normalisation / conv ---
 // y[m, :] = LayerNorm(x[m, :]) * gamma + beta over C channels (eps 1e-5, biased variance).

@@ -25,6 +25,8 @@
 // parent(t) = t & (t-1):
 //     hP[0] = 0;  hP[t] = hP[parent] + exp(A S[t]) * (H[t] - exp(A (S[t]-S[parent])) H[parent])
 // which is evaluated left to right with O(log L) saved ancestors per state.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -259,23 +261,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a
 // lane]) so that the 8 lanes of a phase read 128 contiguous bytes.  The staging threads also
 // pre-compute s = -dt*log2(e) and u = x*dt once per (t, row) instead of once per lane.
 // ------------------------------------------------------------------------------------------
-constexpr int TC2 = 16;   // timesteps per staged chunk
+constexpr int TC2 = 8;    // timesteps per staged chunk
 
 template <int LPR, int WARPS, bool STRUCT>
-__global__ void __launch_bounds__(WARPS * 32) scan_rows2_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, 672 / (WARPS * 32)) scan_rows2_kernel(ScanArgs a) {
   constexpr int N = LPR * SPL;
   constexpr int GROUPS = 32 / LPR;             // lane groups per warp
   constexpr int ROWS = WARPS * GROUPS * 2;     // rows per CTA
   constexpr int THREADS = WARPS * 32;
   constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : 1);
   constexpr int TPL = 8 >> NR;
+  constexpr int NBC = TC2 * (N / 4);           // float4 per chunk of B (and of C)
+  constexpr int NXD = TC2 * ROWS;              // elements per chunk of x (dt, z)
+  constexpr int PBC = (NBC + THREADS - 1) / THREADS;
+  constexpr int PXD = (NXD + THREADS - 1) / THREADS;
 
-  __shared__ __align__(16) float sB[TC2][N];
-  __shared__ __align__(16) float sC[TC2][N];
-  __shared__ __align__(16) float2 ssu[TC2][ROWS];  // (s, u)
-  __shared__ float sx[TC2][ROWS];
-  __shared__ float sz[TC2][ROWS];
-  __shared__ float sy[TC2][ROWS];
+  // two buffers: chunk c+1 is committed into the other buffer while chunk c is being consumed,
+  // so one __syncthreads per chunk suffices
+  __shared__ __align__(16) float sB[2][TC2][N];
+  __shared__ __align__(16) float sC[2][TC2][N];
+  __shared__ __align__(16) float2 ssu[2][TC2][ROWS];  // (s, u)
+  __shared__ float sx[2][TC2][ROWS];
+  __shared__ float sz[2][TC2][ROWS];
+  __shared__ float sy[2][TC2][ROWS];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -286,83 +294,115 @@ __global__ void __launch_bounds__(WARPS * 32) scan_rows2_kernel(ScanArgs a) {
   const int64_t b = blockIdx.y;
   const int64_t L = a.L;
   const bool gate = a.z != nullptr;
+  const int nchunks = (int)((L + TC2 - 1) / TC2);
 
   float al2[SPL];
 #pragma unroll
   for (int k = 0; k < SPL; ++k) al2[k] = a.A[n0 + k] * LOG2E;
   const float n0p1 = (float)(n0 + 1);
+  float Dv[2] = {0.f, 0.f};
+  if (a.D) { Dv[0] = __ldg(a.D + d0 + rl0); Dv[1] = __ldg(a.D + d0 + rl0 + 1); }
 
   State8 H0, H1;
 #pragma unroll
   for (int k = 0; k < 4; ++k) H0.v[k] = H1.v[k] = 0ull;
 
-  for (int64_t tc0 = 0; tc0 < L; tc0 += TC2) {
+  // ---- software pipeline: the global loads of chunk c+1 are in flight while chunk c computes
+  float4 rb[PBC], rc[PBC];
+  float rx[PXD], rd[PXD], rz[PXD];
+  auto prefetch = [&](int c) {
+    const int64_t tc0 = (int64_t)c * TC2;
     const int tcn = (int)((L - tc0) < TC2 ? (L - tc0) : TC2);
-    // ---- stage: B/C permuted so that float4 f = 2*jj + c of a row lands at slot c*LPR + jj
-    for (int idx = tid; idx < TC2 * (N / 4); idx += THREADS) {
+#pragma unroll
+    for (int i = 0; i < PBC; ++i) {
+      const int idx = tid + i * THREADS;
       const int t = idx / (N / 4), f = idx % (N / 4);
-      float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vc = vb;
-      if (t < tcn) {
+      rb[i] = rc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < NBC && t < tcn) {
         const int64_t row = b * L + tc0 + t;
-        vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
-        vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
+        rb[i] = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
+        rc[i] = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
       }
-      const int slot = (f & 1) * LPR + (f >> 1);
-      *reinterpret_cast<float4*>(&sB[t][4 * slot]) = vb;
-      *reinterpret_cast<float4*>(&sC[t][4 * slot]) = vc;
     }
-    for (int idx = tid; idx < TC2 * ROWS; idx += THREADS) {
+#pragma unroll
+    for (int i = 0; i < PXD; ++i) {
+      const int idx = tid + i * THREADS;
       const int t = idx / ROWS, r = idx % ROWS;
-      float vx = 0.f, vd = 0.f, vz = 0.f;
-      if (t < tcn) {
+      rx[i] = rd[i] = rz[i] = 0.f;
+      if (idx < NXD && t < tcn) {
         const int64_t row = b * L + tc0 + t;
-        vx = __ldg(a.x + row * a.ldx + d0 + r);
-        vd = __ldg(a.dt + row * a.lddt + d0 + r);
-        if (gate) vz = __ldg(a.z + row * a.ldz + d0 + r);
+        rx[i] = __ldg(a.x + row * a.ldx + d0 + r);
+        rd[i] = __ldg(a.dt + row * a.lddt + d0 + r);
+        if (gate) rz[i] = __ldg(a.z + row * a.ldz + d0 + r);
       }
-      ssu[t][r] = make_float2(STRUCT ? -vd * LOG2E : vd, vx * vd);
-      sx[t][r] = vx;
-      sz[t][r] = vz;
     }
-    __syncthreads();
+  };
+  // B/C rows are stored permuted: float4 f = 2*jj + c of a row lands at slot c*LPR + jj, so the
+  // 8 lanes of a 16-byte load phase read 128 contiguous bytes
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < PBC; ++i) {
+      const int idx = tid + i * THREADS;
+      if (idx < NBC) {
+        const int t = idx / (N / 4), f = idx % (N / 4);
+        const int slot = (f & 1) * LPR + (f >> 1);
+        *reinterpret_cast<float4*>(&sB[buf][t][4 * slot]) = rb[i];
+        *reinterpret_cast<float4*>(&sC[buf][t][4 * slot]) = rc[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PXD; ++i) {
+      const int idx = tid + i * THREADS;
+      if (idx < NXD) {
+        const int t = idx / ROWS, r = idx % ROWS;
+        ssu[buf][t][r] = make_float2(STRUCT ? -rd[i] * LOG2E : rd[i], rx[i] * rd[i]);
+        sx[buf][t][r] = rx[i];
+        sz[buf][t][r] = rz[i];
+      }
+    }
+  };
 
+  prefetch(0);
+  commit(0);
+  __syncthreads();
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int64_t tc0 = (int64_t)c * TC2;
+    const int tcn = (int)((L - tc0) < TC2 ? (L - tc0) : TC2);
+    const int buf = c & 1;
+    if (c + 1 < nchunks) prefetch(c + 1);
+
+#pragma unroll 1
     for (int g4 = 0; g4 < TC2; g4 += 4) {
-      if (g4 >= tcn) break;
       float yp[8];   // index 2*i + r : step i, row r
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = g4 + i;
-        const float4 su = *reinterpret_cast<const float4*>(&ssu[t][rl0]);   // (s0,u0,s1,u1)
-        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[t][4 * j]);
-        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[t][4 * (LPR + j)]);
-        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * j]);
-        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * (LPR + j)]);
+        const float4 su = *reinterpret_cast<const float4*>(&ssu[buf][t][rl0]);   // (s0,u0,s1,u1)
+        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[buf][t][4 * j]);
+        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[buf][t][4 * (LPR + j)]);
+        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[buf][t][4 * j]);
+        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[buf][t][4 * (LPR + j)]);
         State8 p;
-        u64 uu, acc;
-        // row 0
+        u64 uu, acc, acc2;
         if (STRUCT) powers_structured(su.x, n0p1, p); else powers_generic(su.x, al2, p);
         uu = pack2(su.y, su.y);
         H0.v[0] = fma2(p.v[0], H0.v[0], mul2(uu, b01.x));
         H0.v[1] = fma2(p.v[1], H0.v[1], mul2(uu, b01.y));
         H0.v[2] = fma2(p.v[2], H0.v[2], mul2(uu, b23.x));
         H0.v[3] = fma2(p.v[3], H0.v[3], mul2(uu, b23.y));
-        acc = mul2(H0.v[0], c01.x);
-        acc = fma2(H0.v[1], c01.y, acc);
-        acc = fma2(H0.v[2], c23.x, acc);
-        acc = fma2(H0.v[3], c23.y, acc);
-        yp[2 * i] = hsum2(acc);
-        // row 1
+        acc = fma2(H0.v[1], c01.y, mul2(H0.v[0], c01.x));
+        acc2 = fma2(H0.v[3], c23.y, mul2(H0.v[2], c23.x));
+        yp[2 * i] = hsum2(add2(acc, acc2));
         if (STRUCT) powers_structured(su.z, n0p1, p); else powers_generic(su.z, al2, p);
         uu = pack2(su.w, su.w);
         H1.v[0] = fma2(p.v[0], H1.v[0], mul2(uu, b01.x));
         H1.v[1] = fma2(p.v[1], H1.v[1], mul2(uu, b01.y));
         H1.v[2] = fma2(p.v[2], H1.v[2], mul2(uu, b23.x));
         H1.v[3] = fma2(p.v[3], H1.v[3], mul2(uu, b23.y));
-        acc = mul2(H1.v[0], c01.x);
-        acc = fma2(H1.v[1], c01.y, acc);
-        acc = fma2(H1.v[2], c23.x, acc);
-        acc = fma2(H1.v[3], c23.y, acc);
-        yp[2 * i + 1] = hsum2(acc);
+        acc = fma2(H1.v[1], c01.y, mul2(H1.v[0], c01.x));
+        acc2 = fma2(H1.v[3], c23.y, mul2(H1.v[2], c23.x));
+        yp[2 * i + 1] = hsum2(add2(acc, acc2));
       }
       // transpose-reduce the 8 partials over the LPR lanes of the group
 #pragma unroll
@@ -381,19 +421,20 @@ __global__ void __launch_bounds__(WARPS * 32) scan_rows2_kernel(ScanArgs a) {
 #pragma unroll
       for (int i = 0; i < TPL; ++i) {
         const int v = j * TPL + i;
-        const int t = g4 + (v >> 1), rr = rl0 + (v & 1);
-        float yv = yp[i] + sx[t][rr] * (a.D ? __ldg(a.D + d0 + rr) : 0.f);
+        const int t = g4 + (v >> 1), rr = v & 1;
+        float yv = yp[i] + sx[buf][t][rl0 + rr] * (rr ? Dv[1] : Dv[0]);
         if (gate) {
-          const float zv = sz[t][rr];
+          const float zv = sz[buf][t][rl0 + rr];
           yv *= zv / (1.0f + __expf(-zv));
         }
-        sy[t][rr] = yv;
+        sy[buf][t][rl0 + rr] = yv;
       }
     }
-    __syncthreads();
+    if (c + 1 < nchunks) commit(buf ^ 1);   // other buffer: last read during chunk c-1, before the previous barrier
+    __syncthreads();                        // sy[buf] complete, chunk c+1 visible
     for (int idx = tid; idx < tcn * ROWS; idx += THREADS) {
       const int t = idx / ROWS, r = idx % ROWS;
-      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
+      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[buf][t][r];   // sy[buf] is next written during chunk c+2
     }
   }
 }
