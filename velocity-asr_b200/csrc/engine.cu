@@ -326,7 +326,7 @@ int pack_frontend_impl(vasr_handle* h) {
     default_filterbank(n_mels, fb);
   }
   // DFT table rows: k in [0,201): win[n] cos(2 pi k n / 400); 201 + k: win[n] sin(...)
-  std::vector<float> tab((size_t)2 * N_FREQ * N_FFT);
+  std::vector<float> tab((size_t)SPEC_LD * N_FFT, 0.f);   // 402 rows + 2 zero rows (N % 4 == 0 for the tensor-core path)
   for (int k = 0; k < N_FREQ; ++k)
     for (int n = 0; n < N_FFT; ++n) {
       const double ang = 2.0 * M_PI * (double)((k * n) % N_FFT) / (double)N_FFT;
@@ -506,7 +506,7 @@ int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int 
   GemmArgs g;
   g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
   g.W = h->dft_w; g.C = k.spec; g.ldc = SPEC_LD;
-  g.M = q.B * q.T; g.N = 2 * N_FREQ; g.K = N_FFT;
+  g.M = q.B * q.T; g.N = SPEC_LD; g.K = N_FFT;
   g.blocked_sum = 1;
   RET(gemm(h, g, s));
   KL(launch_mel_log(k.spec, SPEC_LD, k.raw, q.B * q.T, N_FREQ, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, s,
@@ -554,8 +554,8 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   *out = nullptr;
   const vasr_config& c = *cfg;
   if (c.scan_mode < 0 || c.scan_mode > 2) return fail(VASR_ERR_INVALID, "Unknown scan_mode");
-  if (c.d_model <= 0 || c.d_model > 256 || (c.d_model % 16) != 0)
-    return fail(VASR_ERR_UNSUPPORTED, "d_model must be a multiple of 16, at most 256");
+  if (c.d_model <= 0 || c.d_model > 192 || (c.d_model % 16) != 0)
+    return fail(VASR_ERR_UNSUPPORTED, "d_model must be a multiple of 16, at most 192");
   if ((c.mel_bins * 3) % 16 != 0 || c.mel_bins * 8 > 1024)
     return fail(VASR_ERR_UNSUPPORTED, "mel_bins must make 3*mel_bins a multiple of 16 (and be <= 128)");
   auto n_ok = [](int n) { return n == 16 || n == 32 || n == 64; };

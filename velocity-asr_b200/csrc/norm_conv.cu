@@ -58,50 +58,95 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
   }
 }
 
-// One CTA = TT consecutive tokens of one utterance (+ k-1 halo tokens on the left).
-constexpr int TT = 32;
+// One warp = RUN consecutive tokens of one utterance.  The lane keeps its channels of the last
+// k-1 normalised rows in registers (a sliding window), so every input row is read once, every
+// output row written once, and nothing goes through shared memory.  The k-1 rows before the run
+// are re-normalised by the warp (halo).  Rows are fetched two iterations ahead of their use so the
+// global-load latency overlaps the arithmetic of the rows in between.
+constexpr int RUN = 16;
 constexpr int MAXK = 8;
+constexpr int DW_PER = 6;   // channels per lane: C <= 192
 
-__global__ void __launch_bounds__(256) ln_dwconv_kernel(const float* __restrict__ x, float* __restrict__ u,
+template <int K>
+__global__ void __launch_bounds__(128) ln_dwconv_kernel(const float* __restrict__ x, float* __restrict__ u,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ w,
-                                                        const float* __restrict__ bias, int64_t L, int C,
-                                                        int k) {
-  extern __shared__ float sx[];  // (TT + k - 1) x C, normalised rows; rows before t = 0 are zero
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                        const float* __restrict__ bias, int64_t L, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t run = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int64_t b = blockIdx.y;
-  const int64_t t0 = (int64_t)blockIdx.x * TT;
-  const int halo = k - 1;
-  const int rows = TT + halo;
-  for (int r = warp; r < rows; r += 8) {
-    const int64_t t = t0 - halo + r;
-    float v[LN_MAX_PER_LANE];
-    const bool live = t >= 0 && t < L;
-    if (live) {
-      const float* xr = x + (b * L + t) * C;
+  const int64_t t0 = run * RUN;
+  if (t0 >= L) return;
+  float wv[DW_PER][K], bv[DW_PER], gv[DW_PER], be[DW_PER];
 #pragma unroll
-      for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-        int c = lane + 32 * i;
-        v[i] = c < C ? xr[c] : 0.f;
-      }
-      warp_layer_norm<LN_MAX_PER_LANE>(v, C, lane, gamma, beta);
-    }
+  for (int i = 0; i < DW_PER; ++i) {
+    const int c = lane + 32 * i;
+    const bool ok = c < C;
+    bv[i] = ok ? __ldg(bias + c) : 0.f;
+    gv[i] = ok ? __ldg(gamma + c) : 0.f;
+    be[i] = ok ? __ldg(beta + c) : 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
-      int c = lane + 32 * i;
-      if (c < C) sx[r * C + c] = live ? v[i] : 0.f;
-    }
+    for (int j = 0; j < K; ++j) wv[i][j] = ok ? __ldg(w + c * K + j) : 0.f;
   }
-  __syncthreads();
-  // out[t, c] = bias[c] + sum_j w[c, j] * xn[t + j - (k-1), c]  ==  sx[(t - t0) + j][c]
-  for (int idx = threadIdx.x; idx < TT * C; idx += 256) {
-    const int tt = idx / C, c = idx - tt * C;
-    const int64_t t = t0 + tt;
-    if (t >= L) break;
-    float acc = __ldg(bias + c);
-    for (int j = 0; j < k; ++j) acc = fmaf(__ldg(w + c * k + j), sx[(tt + j) * C + c], acc);
-    u[(b * L + t) * C + c] = acc;
+  float win[K][DW_PER];   // win[j] = normalised row t - (K-1) + j ; zero before the utterance starts
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int i = 0; i < DW_PER; ++i) win[j][i] = 0.f;
+
+  const float invC = 1.0f / (float)C;
+  const int64_t tend = (t0 + RUN < L) ? t0 + RUN : L;
+  const float* xb = x + b * L * C;
+  auto fetch = [&](int64_t t, float (&dst)[DW_PER]) {
+#pragma unroll
+    for (int i = 0; i < DW_PER; ++i) {
+      const int c = lane + 32 * i;
+      dst[i] = (t >= 0 && t < tend && c < C) ? __ldg(xb + t * C + c) : 0.f;
+    }
+  };
+  float r0[DW_PER], r1[DW_PER];     // rows t and t+1, in flight
+  fetch(t0 - (K - 1), r0);
+  fetch(t0 - (K - 1) + 1, r1);
+  for (int64_t t = t0 - (K - 1); t < tend; ++t) {
+    float v[DW_PER];
+#pragma unroll
+    for (int i = 0; i < DW_PER; ++i) { v[i] = r0[i]; r0[i] = r1[i]; }
+    fetch(t + 2, r1);
+    // slide
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j)
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) win[j][i] = win[j + 1][i];
+    if (t >= 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) s += v[i];
+      const float mean = warp_sum(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) {
+        const float d = (lane + 32 * i < C) ? v[i] - mean : 0.f;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) * invC + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) win[K - 1][i] = (v[i] - mean) * rstd * gv[i] + be[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) win[K - 1][i] = 0.f;
+    }
+    if (t >= t0) {
+      float* ur = u + (b * L + t) * C;
+#pragma unroll
+      for (int i = 0; i < DW_PER; ++i) {
+        const int c = lane + 32 * i;
+        float acc = bv[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fmaf(wv[i][j], win[j][i], acc);
+        if (c < C) ur[c] = acc;
+      }
+    }
   }
 }
 
@@ -120,10 +165,15 @@ cudaError_t launch_ln_dwconv(const float* x, float* u, const float* gamma, const
                              const float* bias, int64_t B, int64_t L, int C, int k, cudaStream_t s,
                              int64_t* launches) {
   if (B <= 0 || L <= 0) return cudaSuccess;
-  if (C > 32 * LN_MAX_PER_LANE || k < 1 || k > MAXK || B > 65535) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)((L + TT - 1) / TT), (unsigned)B);
-  size_t smem = (size_t)(TT + k - 1) * C * sizeof(float);
-  ln_dwconv_kernel<<<grid, 256, smem, s>>>(x, u, gamma, beta, w, bias, L, C, k);
+  if (C > 32 * DW_PER || k < 1 || k > MAXK || B > 65535) return cudaErrorInvalidValue;
+  const int64_t runs = (L + RUN - 1) / RUN;
+  dim3 grid((unsigned)((runs + 3) / 4), (unsigned)B);
+  switch (k) {
+#define VASR_DW_CASE(KK) case KK: ln_dwconv_kernel<KK><<<grid, 128, 0, s>>>(x, u, gamma, beta, w, bias, L, C); break;
+    VASR_DW_CASE(1) VASR_DW_CASE(2) VASR_DW_CASE(3) VASR_DW_CASE(4)
+    VASR_DW_CASE(5) VASR_DW_CASE(6) VASR_DW_CASE(7) VASR_DW_CASE(8)
+#undef VASR_DW_CASE
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }

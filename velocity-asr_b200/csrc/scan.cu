@@ -35,7 +35,6 @@ namespace vasr {
 namespace {
 
 constexpr int SPL = 8;             // states per lane
-constexpr int TC = 32;             // timesteps per staged chunk
 constexpr int SCAN_THREADS = 128;
 constexpr int NLEV = 26;           // ancestor levels of the quirk mode (L < 2^24)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -61,23 +60,37 @@ __device__ __forceinline__ void powers_generic(float s, const float (&al2)[SPL],
   for (int k = 0; k < 4; ++k) p.v[k] = pack2(ex2_approx(s * al2[2 * k]), ex2_approx(s * al2[2 * k + 1]));
 }
 
-template <int LPR, bool QUIRK, bool STRUCT>
-__global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a) {
+// ------------------------------------------------------------------------------------------
+// The reference's 'parallel' scan (quirk).  One row per lane group (8 states per lane).  Steps are
+// taken eight at a time, aligned to multiples of 8, so the ancestor an index needs is known at
+// compile time for seven of the eight steps:  parent(8q+i) = 8q + (i & (i-1)).  Ancestor levels
+// 1..3 ("most recent index with at least l trailing zeros") therefore live in registers; only the
+// step at 8q touches the higher levels, which sit in local memory (one read, ~one write per 8 steps).
+// ------------------------------------------------------------------------------------------
+constexpr int TCQ = 16;
+
+struct Anc {
+  State8 hp, H;
+  double S;
+};
+
+template <int LPR, bool STRUCT>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   constexpr int N = LPR * SPL;
   constexpr int ROWS = SCAN_THREADS / LPR;
   constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : (LPR == 2 ? 1 : 0));
-  constexpr int TPL = 8 >> NR;  // finished timesteps per lane after the transpose-reduce
+  constexpr int TPL = 8 >> NR;
+  constexpr int HL = NLEV - 4;   // levels >= 4
 
-  __shared__ __align__(16) float sB[TC][N];
-  __shared__ __align__(16) float sC[TC][N];
-  __shared__ float sx[TC][ROWS];
-  __shared__ float sdt[TC][ROWS];
-  __shared__ float sz[TC][ROWS];
-  __shared__ float sy[TC][ROWS];
+  __shared__ __align__(16) float sB[TCQ][N];
+  __shared__ __align__(16) float sC[TCQ][N];
+  __shared__ float sx[TCQ][ROWS];
+  __shared__ float sdt[TCQ][ROWS];
+  __shared__ float sz[TCQ][ROWS];
+  __shared__ float sy[TCQ][ROWS];
 
   const int tid = threadIdx.x;
-  const int rl = tid / LPR;   // row within the CTA
-  const int j = tid % LPR;    // lane within the row
+  const int rl = tid / LPR, j = tid % LPR;
   const int n0 = j * SPL;
   const int d0 = blockIdx.x * ROWS;
   const int64_t b = blockIdx.y;
@@ -90,38 +103,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a
   const float n0p1 = (float)(n0 + 1);
   const float Dd = a.D ? a.D[d0 + rl] : 0.f;
 
-  State8 H;
+  Anc cur, a1, a2, a3;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) H.v[k] = 0ull;
-
-  // quirk-mode ancestors (local memory; touched ~2 levels per step)
-  float anc_hp[QUIRK ? NLEV : 1][SPL];
-  float anc_H[QUIRK ? NLEV : 1][SPL];
-  double anc_S[QUIRK ? NLEV : 1];
-  double S = 0.0;
-  if (QUIRK) {
-    for (int l = 0; l < NLEV; ++l) {
-      anc_S[l] = 0.0;
+  for (int k = 0; k < 4; ++k) cur.hp.v[k] = cur.H.v[k] = 0ull;
+  cur.S = 0.0;
+  a1 = a2 = a3 = cur;
+  float hi_hp[HL][SPL], hi_H[HL][SPL];
+  double hi_S[HL];
+  for (int l = 0; l < HL; ++l) {
+    hi_S[l] = 0.0;
 #pragma unroll
-      for (int k = 0; k < SPL; ++k) anc_hp[l][k] = anc_H[l][k] = 0.f;
-    }
+    for (int k = 0; k < SPL; ++k) hi_hp[l][k] = hi_H[l][k] = 0.f;
   }
 
-  for (int64_t tc0 = 0; tc0 < L; tc0 += TC) {
-    const int tcn = (int)((L - tc0) < TC ? (L - tc0) : TC);
-    // ---- stage the chunk
-    for (int idx = tid; idx < TC * (N / 4); idx += SCAN_THREADS) {
-      const int t = idx / (N / 4), c4 = (idx % (N / 4)) * 4;
+  for (int64_t tc0 = 0; tc0 < L; tc0 += TCQ) {
+    const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
+    for (int idx = tid; idx < TCQ * (N / 4); idx += SCAN_THREADS) {
+      const int t = idx / (N / 4), f = idx % (N / 4);
       float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vc = vb;
       if (t < tcn) {
         const int64_t row = b * L + tc0 + t;
-        vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + c4));
-        vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + c4));
+        vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
+        vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
       }
-      *reinterpret_cast<float4*>(&sB[t][c4]) = vb;
-      *reinterpret_cast<float4*>(&sC[t][c4]) = vc;
+      const int slot = (f & 1) * LPR + (f >> 1);   // conflict-free 16-byte phases (see below)
+      *reinterpret_cast<float4*>(&sB[t][4 * slot]) = vb;
+      *reinterpret_cast<float4*>(&sC[t][4 * slot]) = vc;
     }
-    for (int idx = tid; idx < TC * ROWS; idx += SCAN_THREADS) {
+    for (int idx = tid; idx < TCQ * ROWS; idx += SCAN_THREADS) {
       const int t = idx / ROWS, r = idx % ROWS;
       float vx = 0.f, vd = 0.f, vz = 0.f;
       if (t < tcn) {
@@ -136,84 +145,95 @@ __global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a
     }
     __syncthreads();
 
-    // ---- eight timesteps at a time
-    for (int g8 = 0; g8 < TC; g8 += 8) {
+#pragma unroll 1
+    for (int g8 = 0; g8 < TCQ; g8 += 8) {
       if (g8 >= tcn) break;
       float yp[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      // one step: hP from `par`, output partial, then the true-recurrence update of cur.H / cur.S
+      auto step = [&](int i, const Anc& par, bool has_parent) {
         const int t = g8 + i;
         const float dtv = sdt[t][rl];
         const float xv = sx[t][rl];
-        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][n0]);
-        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][n0 + 4]);
-
-        if (QUIRK) {
-          const int64_t tg = tc0 + t;
-          State8 hp;
-          if (tg == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hp.v[k] = 0ull;
+        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * j]);
+        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * (LPR + j)]);
+        if (has_parent) {
+          const float Sf = (float)cur.S;
+          const float dS = (float)(cur.S - par.S);
+          State8 q, pd;
+          if (STRUCT) {
+            powers_structured(-Sf * LOG2E, n0p1, q);
+            powers_structured(-dS * LOG2E, n0p1, pd);
           } else {
-            const int tz = __ffsll((long long)tg) - 1;
-            const int pl = tz + 1;
-            const float Sf = (float)S;
-            const float dS = (float)(S - anc_S[pl]);
-            State8 q, pd;
-            if (STRUCT) {
-              powers_structured(-Sf * LOG2E, n0p1, q);
-              powers_structured(-dS * LOG2E, n0p1, pd);
-            } else {
-              powers_generic(Sf, al2, q);
-              powers_generic(dS, al2, pd);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const u64 npH = pack2(-anc_H[pl][2 * k], -anc_H[pl][2 * k + 1]);
-              const u64 php = pack2(anc_hp[pl][2 * k], anc_hp[pl][2 * k + 1]);
-              // inner = H - pd * pH ; hp = php + q * inner
-              const u64 inner = fma2(pd.v[k], npH, H.v[k]);
-              hp.v[k] = fma2(q.v[k], inner, php);
-            }
-            for (int l = 0; l <= tz; ++l) {
-              anc_S[l] = S;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                unpack2(hp.v[k], anc_hp[l][2 * k], anc_hp[l][2 * k + 1]);
-                unpack2(H.v[k], anc_H[l][2 * k], anc_H[l][2 * k + 1]);
-              }
-            }
+            powers_generic(Sf, al2, q);
+            powers_generic(dS, al2, pd);
           }
-          u64 acc = mul2(hp.v[0], c01.x);
-          acc = fma2(hp.v[1], c01.y, acc);
-          acc = fma2(hp.v[2], c23.x, acc);
-          acc = fma2(hp.v[3], c23.y, acc);
-          yp[i] = hsum2(acc);
-          S += (double)dtv;
+          const u64 neg1 = pack2(-1.f, -1.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const u64 inner = fma2(mul2(pd.v[k], neg1), par.H.v[k], cur.H.v[k]);   // H - pd * H[parent]
+            cur.hp.v[k] = fma2(q.v[k], inner, par.hp.v[k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cur.hp.v[k] = 0ull;
         }
-
-        // true recurrence step: H <- p * H + (x dt) * B
+        u64 acc = fma2(cur.hp.v[1], c01.y, mul2(cur.hp.v[0], c01.x));
+        u64 acc2 = fma2(cur.hp.v[3], c23.y, mul2(cur.hp.v[2], c23.x));
+        yp[i] = hsum2(add2(acc, acc2));
+      };
+      auto advance = [&](int i) {
+        const int t = g8 + i;
+        const float dtv = sdt[t][rl];
         State8 p;
         if (STRUCT) powers_structured(-dtv * LOG2E, n0p1, p);
         else powers_generic(dtv, al2, p);
-        const float u = xv * dtv;
+        const float u = sx[t][rl] * dtv;
         const u64 uu = pack2(u, u);
-        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[t][n0]);
-        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[t][n0 + 4]);
-        H.v[0] = fma2(p.v[0], H.v[0], mul2(uu, b01.x));
-        H.v[1] = fma2(p.v[1], H.v[1], mul2(uu, b01.y));
-        H.v[2] = fma2(p.v[2], H.v[2], mul2(uu, b23.x));
-        H.v[3] = fma2(p.v[3], H.v[3], mul2(uu, b23.y));
-        if (!QUIRK) {
-          u64 acc = mul2(H.v[0], c01.x);
-          acc = fma2(H.v[1], c01.y, acc);
-          acc = fma2(H.v[2], c23.x, acc);
-          acc = fma2(H.v[3], c23.y, acc);
-          yp[i] = hsum2(acc);
-        }
-      }
+        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[t][4 * j]);
+        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[t][4 * (LPR + j)]);
+        cur.H.v[0] = fma2(p.v[0], cur.H.v[0], mul2(uu, b01.x));
+        cur.H.v[1] = fma2(p.v[1], cur.H.v[1], mul2(uu, b01.y));
+        cur.H.v[2] = fma2(p.v[2], cur.H.v[2], mul2(uu, b23.x));
+        cur.H.v[3] = fma2(p.v[3], cur.H.v[3], mul2(uu, b23.y));
+        cur.S += (double)dtv;
+      };
 
-      // ---- transpose-reduce over the LPR lanes of the row
+      // ---- i = 0 : index 8q, ancestor level >= 4 (dynamic)
+      {
+        const int64_t tg = tc0 + g8;
+        if (tg == 0) {
+          step(0, cur, false);
+        } else {
+          const int z = 3 + (__ffsll((long long)(tg >> 3)) - 1);
+          const int pl = z + 1 - 4;
+          Anc par;
+          par.S = hi_S[pl];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            par.hp.v[k] = pack2(hi_hp[pl][2 * k], hi_hp[pl][2 * k + 1]);
+            par.H.v[k] = pack2(hi_H[pl][2 * k], hi_H[pl][2 * k + 1]);
+          }
+          step(0, par, true);
+          for (int l = 4; l <= z; ++l) {
+            hi_S[l - 4] = cur.S;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              unpack2(cur.hp.v[k], hi_hp[l - 4][2 * k], hi_hp[l - 4][2 * k + 1]);
+              unpack2(cur.H.v[k], hi_H[l - 4][2 * k], hi_H[l - 4][2 * k + 1]);
+            }
+          }
+          a1 = a2 = a3 = cur;
+        }
+        advance(0);
+      }
+      step(1, a1, true); advance(1);
+      step(2, a2, true); a1 = cur; advance(2);
+      step(3, a1, true); advance(3);
+      step(4, a3, true); a1 = a2 = cur; advance(4);
+      step(5, a1, true); advance(5);
+      step(6, a2, true); a1 = cur; advance(6);
+      step(7, a1, true); advance(7);
+
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const int lane_bit = LPR >> (r + 1);
@@ -226,7 +246,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a
           yp[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
         }
       }
-      // lane j now owns timesteps g8 + j*TPL + i, i < TPL: skip term, gate, stage for the store
 #pragma unroll
       for (int i = 0; i < TPL; ++i) {
         const int t = g8 + j * TPL + i;
@@ -239,16 +258,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) selective_scan_kernel(ScanArgs a
       }
     }
     __syncthreads();
-    // ---- store the chunk
     for (int idx = tid; idx < tcn * ROWS; idx += SCAN_THREADS) {
       const int t = idx / ROWS, r = idx % ROWS;
       a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
     }
-    // the next chunk's staging does not touch sy, and its first __syncthreads orders the
-    // sy reads above before the next writes to sy.
   }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Fast path of the true recurrence (scan_mode sequential / mamba).
@@ -466,8 +481,8 @@ cudaError_t launch_lpr(const ScanArgs& a, cudaStream_t s) {
   if (a.Di % ROWS != 0) return cudaErrorInvalidValue;
   dim3 grid((unsigned)(a.Di / ROWS), (unsigned)a.B);
   if (!a.parallel_quirk) return launch_recurrence<LPR>(a, s);
-  if (a.structured_a) selective_scan_kernel<LPR, true, true><<<grid, SCAN_THREADS, 0, s>>>(a);
-  else selective_scan_kernel<LPR, true, false><<<grid, SCAN_THREADS, 0, s>>>(a);
+  if (a.structured_a) scan_quirk_kernel<LPR, true><<<grid, SCAN_THREADS, 0, s>>>(a);
+  else scan_quirk_kernel<LPR, false><<<grid, SCAN_THREADS, 0, s>>>(a);
   return cudaGetLastError();
 }
 
