@@ -133,9 +133,13 @@ int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float
                 float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream);
 
 /* Same contract through the tensor-core kernel (tcgen05 + TMEM + TMA, 3xTF32 split): the
- * kernel every token-sized projection of the model runs on.  K % 4 == 0. */
-int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev,
-                   float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream);
+ * kernel every token-sized projection of the model runs on.  K % 4 == 0, N % 4 == 0.
+ * The kernel reads the weight as two TF32 matrices [hi | lo] (2*N*K floats) made by
+ * vasr_split_tf32; pass w_split_dev = NULL to have the call split w_dev on the fly. */
+int vasr_split_tf32(const float* w_dev, float* split_dev, int64_t numel, void* stream);
+int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* w_split_dev,
+                   const float* bias_dev, float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N,
+                   int act, void* stream);
 
 /* ---- bookkeeping for the bench: kernels launched by this handle since creation, and the
  * share of the last vasr_transcribe spent in the scan (device ms, CUDA events on `stream`)

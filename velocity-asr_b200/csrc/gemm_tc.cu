@@ -1,24 +1,34 @@
 // gemm_tc.cu — tensor-core projection kernel for sm_100a: C = epi(A · Wᵀ) with fp32-grade accuracy.
 //
-// tcgen05.mma (kind::tf32) issued by one thread, operands staged in shared memory by TMA
-// (128-byte swizzle), accumulators in TMEM, read back with tcgen05.ld for a fused epilogue.
+// tcgen05.mma (kind::tf32) issued by one thread; the weight operand is staged in shared memory
+// by TMA (128-byte swizzle), the activation operand is fed from TENSOR MEMORY, accumulators live
+// in TMEM and are read back with tcgen05.ld for a fused, coalesced epilogue.
 //
 // Accuracy.  One TF32 pass carries ~1e-3 relative error, which flips ~0.3 % of the CTC argmaxes
-// (SURVEY.md section 7.3c).  Each fp32 operand is therefore split exactly into hi + lo, both
-// representable in TF32 (hi = top 19 bits, lo = top 19 bits of the remainder), and every k-step
-// issues three MMAs, A_hi·W_hi + A_lo·W_hi + A_hi·W_lo, accumulated in fp32 in TMEM (error
-// ~2^-21 per product).  Both tiles are split in shared memory by four converter warps between the
-// TMA arrival and the MMA issue (in place for hi, a second buffer for lo), so neither activations
-// nor weights carry a second copy through HBM / L2: TMA moves 32 KB per k-step, not 64.
+// (SURVEY.md section 7.3c).  Each fp32 operand is therefore split into hi + lo, both TF32 values
+// (hi = rna_tf32(x), lo = rna_tf32(x - hi); round-to-nearest keeps the residual error unbiased, which
+// matters for the 400-term DFT rows), and every k-step issues three MMAs,
+// A_lo·W_hi + A_hi·W_lo + A_hi·W_hi, accumulated in fp32 in TMEM (error ~2^-22 per product).
+//
+// Where the split happens (round-1 ncu: the first version split both tiles in shared memory and was
+// bound by shared-memory bandwidth — TMA write + converter read/write + 3x MMA operand reads):
+//   * weights are split ONCE (launch_split_tf32, cached per weight matrix by the engine) and TMA
+//     brings W_hi and W_lo tiles straight from L2;
+//   * the activation tile arrives as raw fp32; four converter warps read it once (one row per
+//     thread = one TMEM lane), split it in registers and tcgen05.st the hi and lo halves into TMEM,
+//     from where the MMA reads its A operand.  Shared memory then carries only the TMA writes, one
+//     read of A and the MMA reads of W.
 //
 // Structure (persistent, one CTA per SM, 14 warps):
-//   warp 0      TMA producer      : A tile and W tile (128 x 32 fp32 each) per stage
+//   warp 0      TMA producer      : A (128 x 32 fp32), W_hi and W_lo (128 x 32) per stage, 4 stages
 //   warp 1      MMA issuer        : 12 tcgen05.mma per stage; tcgen05.commit frees the stage
-//   warps 2-5   converters        : exact hi/lo split of both tiles, fence.proxy.async, arrive
-//   warps 6-13  epilogue          : TMEM -> registers -> bias/act/pos-enc/residual -> global store
-// Two TMEM accumulators (2 x 128 columns) let the epilogue of tile i overlap the mainloop of
-// tile i+1.  Rows of A may come from a strided / overlapping batched view (conv and STFT frames),
-// addressed with a 3-D tensor map (k, row-in-batch, batch); M tiles never straddle a batch.
+//   warps 2-5   converters        : smem A row -> hi/lo -> TMEM (64 columns per stage)
+//   warps 6-13  epilogue          : TMEM -> registers -> per-warp smem transpose -> bias / act /
+//                                   pos-enc / residual on 128-byte row segments -> coalesced stores
+// TMEM map (512 columns): [0,256) two 128-column accumulators (the epilogue of tile i overlaps the
+// mainloop of tile i+1); [256,512) four A stages of 32 hi + 32 lo columns.
+// Rows of A may come from a strided / overlapping batched view (conv and STFT frames), addressed
+// with a 3-D tensor map (k, row-in-batch, batch); M tiles never straddle a batch.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,16 +38,27 @@ namespace vasr {
 
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32, STAGES = 3;
+constexpr int TBM = 128, TBN = 128, TBK = 32, STAGES = 4;
 constexpr int TILE_BYTES = TBM * TBK * 4;            // 16 KB (A and W tiles are the same size)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi | A_lo | W_hi | W_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;          // A | W_hi | W_lo
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 128;            // one 32 x 32 fp32 chunk per epilogue warp
+constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
 constexpr int TC_THREADS = 448;                      // 1 TMA + 1 MMA + 4 converter + 8 epilogue warps
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_A0 = 256;                    // first A column
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+
+// barrier indices
+constexpr int B_FULL = 0, B_CONV = STAGES, B_EMPTY = 2 * STAGES, B_TFULL = 3 * STAGES, B_TEMPTY = 3 * STAGES + 2;
+constexpr int N_BARS = 3 * STAGES + 4;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13),
 // K-major A and B, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TBN >> 3) << 17) | ((TBM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,12 +106,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] · B[smem]ᵀ : 128 x N x 8, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -111,6 +134,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// round-to-nearest TF32 (ties away), low 13 bits cleared
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 
 template <int ACT>
 __device__ __forceinline__ float apply_act_t(float v) {
@@ -129,24 +170,23 @@ struct TcArgs {
   float* C;
   int64_t ldc;
   const float* bias;
-  int act, act_from;
+  int act_from;
   const float* resid;
   int64_t ldr;
   const float* pe_time;
   const float* pe_freq;
   int pe_half;
-  int64_t pe_rows;
 };
 
 template <int ACT, bool PE, bool RESID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+               const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from smem_raw (no integer round trip) so accesses compile to LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  // barrier map: full[s] = 0..2, conv[s] = 3..5, empty[s] = 6..8, tfull[a] = 9..10, tempty[a] = 11..12
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -155,13 +195,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(BAR(s), 1);          // full: producer's expect_tx arrive
-      mbar_init(BAR(3 + s), 128);    // conv: every converter thread
-      mbar_init(BAR(6 + s), 1);      // empty: tcgen05.commit
+      mbar_init(BAR(B_FULL + s), 1);       // producer's expect_tx arrive
+      mbar_init(BAR(B_CONV + s), 128);     // every converter thread
+      mbar_init(BAR(B_EMPTY + s), 1);      // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(BAR(9 + a), 1);      // tmem full: tcgen05.commit
-      mbar_init(BAR(11 + a), 256);   // tmem empty: every epilogue thread
+      mbar_init(BAR(B_TFULL + a), 1);               // tcgen05.commit
+      mbar_init(BAR(B_TEMPTY + a), EPI_WARPS * 32); // every epilogue thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -188,11 +228,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int batch = (int)(mt / g.m_tiles_per_batch);
         const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(BAR(6 + stage), phase ^ 1);
+          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
           const uint32_t sb = stage0 + stage * STAGE_BYTES;
-          mbar_expect_tx(BAR(stage), 2 * TILE_BYTES);
-          tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(stage));
-          tma_load_2d(sb + 2 * TILE_BYTES, &tmW, kb * TBK, nt * TBN, BAR(stage));
+          mbar_expect_tx(BAR(B_FULL + stage), 3 * TILE_BYTES);
+          tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(B_FULL + stage));
+          tma_load_2d(sb + TILE_BYTES, &tmWh, kb * TBK, nt * TBN, BAR(B_FULL + stage));
+          tma_load_2d(sb + 2 * TILE_BYTES, &tmWl, kb * TBK, nt * TBN, BAR(B_FULL + stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -202,116 +243,144 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = (int)(tile % g.n_tiles);
+      // columns of this tile that exist, rounded up to the MMA's N granularity (16)
+      int64_t nrem = g.N - (int64_t)nt * TBN;
+      const uint32_t n_mma = nrem >= TBN ? (uint32_t)TBN : (uint32_t)((nrem + 15) & ~15LL);
+      const uint32_t idesc = make_idesc(n_mma);
       const uint32_t acc = (uint32_t)(it & 1);
-      mbar_wait(BAR(11 + acc), (uint32_t)((it >> 1) & 1) ^ 1);
+      mbar_wait(BAR(B_TEMPTY + acc), (uint32_t)((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * TBN;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(BAR(3 + stage), phase);
+        mbar_wait(BAR(B_FULL + stage), phase);    // W tiles landed (async proxy)
+        mbar_wait(BAR(B_CONV + stage), phase);    // A hi/lo are in TMEM
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = stage0 + stage * STAGE_BYTES;
-          const uint64_t da_hi = umma_desc(sb), da_lo = umma_desc(sb + TILE_BYTES);
-          const uint64_t db_hi = umma_desc(sb + 2 * TILE_BYTES), db_lo = umma_desc(sb + 3 * TILE_BYTES);
+          const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + 2 * TILE_BYTES);
+          const uint32_t a_hi = tmem_base + TMEM_A0 + stage * 64, a_lo = a_hi + 32;
 #pragma unroll
           for (int k4 = 0; k4 < TBK / 8; ++k4) {
             const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
-            umma_tf32(tmem_d, da_lo + adv, db_hi + adv, (kb | k4) != 0);
-            umma_tf32(tmem_d, da_hi + adv, db_lo + adv, 1);
-            umma_tf32(tmem_d, da_hi + adv, db_hi + adv, 1);
+            umma_tf32_ts(tmem_d, a_lo + 8 * k4, db_hi + adv, idesc, (kb | k4) != 0);
+            umma_tf32_ts(tmem_d, a_hi + 8 * k4, db_lo + adv, idesc, 1);
+            umma_tf32_ts(tmem_d, a_hi + 8 * k4, db_hi + adv, idesc, 1);
           }
-          umma_commit(BAR(6 + stage));
-          if (kb == nkb - 1) umma_commit(BAR(9 + acc));
+          umma_commit(BAR(B_EMPTY + stage));
+          if (kb == nkb - 1) umma_commit(BAR(B_TFULL + acc));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < 6) {
-    // ===================== converters: exact hi/lo split of the A tile =====================
-    const int ct = threadIdx.x - 64;   // 0..127
+    // ===================== converters: A row -> (hi, lo) -> TMEM =====================
+    // Thread = one row of the tile = one TMEM lane (a warp may touch lanes 32*(warp%4) .. +31).
+    // Row r of the swizzled tile is 128 contiguous bytes whose 16-byte chunk c sits at c ^ (r & 7):
+    // the eight lanes of a load phase hit eight different chunks, so the reads are conflict-free.
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
     uint32_t stage = 0, phase = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(BAR(stage), phase);
+        mbar_wait(BAR(B_FULL + stage), phase);
+        const uint8_t* arow = smem + stage * STAGE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int tile2 = 0; tile2 < 2; ++tile2) {       // 0: A (hi at +0, lo at +1), 1: W (hi at +2, lo at +3)
-          float4* __restrict__ hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + 2 * tile2 * TILE_BYTES);
-          float4* __restrict__ lo = hi + TILE_BYTES / 16;
-          float4 v[TILE_BYTES / 16 / 128];
-#pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) v[i] = hi[ct + 128 * i];
-#pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u); l.x = v[i].x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u); l.y = v[i].y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u); l.z = v[i].z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u); l.w = v[i].w - h.w;
-            hi[ct + 128 * i] = h;
-            lo[ct + 128 * i] = l;
-          }
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          hi[4 * c + 0] = rna_tf32(v.x); lo[4 * c + 0] = rna_tf32(v.x - __uint_as_float(hi[4 * c + 0]));
+          hi[4 * c + 1] = rna_tf32(v.y); lo[4 * c + 1] = rna_tf32(v.y - __uint_as_float(hi[4 * c + 1]));
+          hi[4 * c + 2] = rna_tf32(v.z); lo[4 * c + 2] = rna_tf32(v.z - __uint_as_float(hi[4 * c + 2]));
+          hi[4 * c + 3] = rna_tf32(v.w); lo[4 * c + 3] = rna_tf32(v.w - __uint_as_float(hi[4 * c + 3]));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(BAR(3 + stage));
+        // the TMEM slot of this stage was last read by MMAs whose commit released `empty[stage]`,
+        // which the producer waited on before the TMA that completed `full[stage]`
+        tc_fence_after();
+        tmem_st32(lane_addr + stage * 64, hi);
+        tmem_st32(lane_addr + stage * 64 + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(BAR(B_CONV + stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ===================== epilogue =====================
-    // A thread owns one output row (TMEM lane = row): it reads 32 accumulator columns at a time and
-    // writes its own 128-byte row segment as eight 16-byte stores.  ACT / PE / RESID are template
-    // parameters, so the loops below carry no per-element branches.
+    // A warp reads a 32-row x 32-column chunk of the accumulator (thread = row), transposes it
+    // through its private 4 KB of shared memory (16-byte chunks XOR-swizzled by row: conflict-free
+    // both ways) and then owns 128-byte row segments: lane l handles columns 4*(l&7).. of rows
+    // (l>>3) + 4*i, so bias / activation / pos-enc / residual and the store are all coalesced.
     const int q = warp & 3;                         // TMEM lane quadrant this warp may read
     const int chalf = (warp - 6) >> 2;              // which two of the four 32-column chunks
+    uint8_t* stg = smem + STAGES * STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES;
+    const int cc = lane & 7, rsub = lane >> 3;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = (int)(tile % g.n_tiles);
       const int64_t mt = tile / g.n_tiles;
       const int64_t batch = mt / g.m_tiles_per_batch;
-      const int64_t mi = (mt % g.m_tiles_per_batch) * TBM + q * 32 + lane;   // row within the batch
-      const bool row_ok = mi < g.rows_per_batch;
-      const int64_t m = batch * g.rows_per_batch + mi;
+      const int64_t mi0 = (mt % g.m_tiles_per_batch) * TBM + q * 32;    // first row (within the batch) of this warp
       const int64_t ncol0 = (int64_t)nt * TBN;
-      float* crow = g.C + m * g.ldc + ncol0;
-      const float* rrow = RESID ? g.resid + m * g.ldr + ncol0 : nullptr;
-      const float* prow = PE ? g.pe_time + mi * g.pe_half : nullptr;
+      const int64_t nrem = g.N - ncol0;
+      const int nchunks = nrem >= TBN ? 4 : (int)((nrem + 31) >> 5);    // 32-column chunks that hold real columns
       const uint32_t acc = (uint32_t)(it & 1);
-      mbar_wait(BAR(9 + acc), (uint32_t)((it >> 1) & 1));
+      mbar_wait(BAR(B_TFULL + acc), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
+      if (c_begin >= c_end) {       // nothing of this tile belongs to this warp: hand the accumulator back
+        tc_fence_before();
+        mbar_arrive(BAR(B_TEMPTY + acc));
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
-        if (c == 2 * chalf + 1) {      // this warp's share of the accumulator is read: hand it back
+        if (c == c_end - 1) {       // this warp's share of the accumulator is in registers
           tc_fence_before();
-          mbar_arrive(BAR(11 + acc));
+          mbar_arrive(BAR(B_TEMPTY + acc));
         }
-        if (!row_ok) continue;
+        {
+          uint8_t* srow = stg + lane * 128;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int64_t n = ncol0 + c * 32 + 4 * k;
-          if (n >= g.N) break;        // N % 4 == 0: a group of four columns is valid or not as a whole
-          float4 x = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
-                                 __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
-          if (g.bias) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-          }
-          if (ACT != ACT_NONE && n >= g.act_from) {
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+        __syncwarp();
+        const int64_t n = ncol0 + c * 32 + 4 * cc;      // this lane's four columns
+        const bool col_ok = n < g.N;                     // N % 4 == 0: the group is valid or not as a whole
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
+        if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
+        const bool act_on = ACT != ACT_NONE && n >= g.act_from;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rsub;
+          const int64_t mi = mi0 + rr;
+          float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          if (!col_ok || mi >= g.rows_per_batch) continue;
+          const int64_t m = batch * g.rows_per_batch + mi;
+          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (act_on) {
             x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
             x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
           }
           if (PE) {
-            const float4 p4 = __ldg(reinterpret_cast<const float4*>(n < g.pe_half ? prow + n : g.pe_freq + (n - g.pe_half)));
+            float4 p4 = pf4;
+            if (n < g.pe_half) p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + mi * g.pe_half + n));
             x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
           }
           if (RESID) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + c * 32 + 4 * k));
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(g.resid + m * g.ldr + n));
             x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
           }
-          *reinterpret_cast<float4*>(crow + c * 32 + 4 * k) = x;
+          *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = x;
         }
+        __syncwarp();               // the staging chunk is rewritten by the next iteration
       }
     }
   }
@@ -322,6 +391,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
+}
+
+// w (n) -> hl[0..n) = rna_tf32(w), hl[n..2n) = rna_tf32(w - hi)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hl,
+                                                         int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  const float h = __uint_as_float(rna_tf32(x));
+  hl[i] = h;
+  hl[n + i] = __uint_as_float(rna_tf32(x - h));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -361,9 +441,9 @@ bool make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dim
 bool gemm_tc_supported(const GemmArgs& g) {
   if (!encode_fn()) return false;
   if (g.K % 4 != 0 || g.lda % 4 != 0 || g.batch_stride % 4 != 0) return false;
-  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) return false;
-  // the epilogue moves 16-byte groups of four columns
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(g.A) || !al16(g.W_split)) return false;
+  // the epilogue moves 16-byte groups of four columns
   if ((g.N & 3) || (g.ldc & 3) || !al16(g.C) || (g.act_from & 3)) return false;
   if (g.bias && !al16(g.bias)) return false;
   if (g.resid && ((g.ldr & 3) || !al16(g.resid))) return false;
@@ -371,18 +451,24 @@ bool gemm_tc_supported(const GemmArgs& g) {
   return true;
 }
 
+cudaError_t launch_split_tf32(const float* w, float* hl, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, hl, n);
+  return cudaGetLastError();
+}
+
 // Returns cudaErrorNotSupported when the tensor maps cannot be encoded (the caller then uses the
-// CUDA-core kernel); any other error is a real launch failure.
+// CUDA-core kernel); any other error is a real launch failure.  g.W_split = [W_hi | W_lo].
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64_t* launches) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  if (!gemm_tc_supported(g)) return cudaErrorNotSupported;
+  if (!g.W_split || !gemm_tc_supported(g)) return cudaErrorNotSupported;
   const int64_t rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
   const int64_t nb = g.rows_per_batch > 0 ? g.M / g.rows_per_batch : 1;
   if (nb * rpb != g.M) return cudaErrorNotSupported;
   if (g.pe_time && g.pe_rows != rpb) return cudaErrorNotSupported;   // pos-enc row == row within the batch
   const int64_t bstride = g.rows_per_batch > 0 ? g.batch_stride : rpb * g.lda;
 
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmWh, tmWl;
   {
     const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)rpb, (uint64_t)nb};
     const uint64_t str[2] = {(uint64_t)g.lda * 4, (uint64_t)(bstride > 0 ? bstride : g.lda) * 4};
@@ -393,7 +479,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.K * 4};
     const uint32_t box[2] = {TBK, TBN};
-    if (!make_map(&tmW, g.W, 2, dims, str, box)) return cudaErrorNotSupported;
+    if (!make_map(&tmWh, g.W_split, 2, dims, str, box)) return cudaErrorNotSupported;
+    if (!make_map(&tmWl, g.W_split + g.N * g.K, 2, dims, str, box)) return cudaErrorNotSupported;
   }
   TcArgs a;
   a.M = g.M; a.N = g.N; a.K = g.K;
@@ -401,9 +488,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.n_batches = nb;
   a.m_tiles_per_batch = (int)((rpb + TBM - 1) / TBM);
   a.n_tiles = (int)((g.N + TBN - 1) / TBN);
-  a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act = g.act; a.act_from = g.act_from;
+  a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act_from = g.act_from;
   a.resid = g.resid; a.ldr = g.ldr;
-  a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half; a.pe_rows = g.pe_rows;
+  a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
@@ -411,7 +498,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   cudaError_t err = cudaSuccess;
   auto go = [&](auto kernel) {
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmW, a);
+    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
   };
 #define VASR_TC_CASE(ACTV)                                                  \
   if (g.act == ACTV) {                                                      \

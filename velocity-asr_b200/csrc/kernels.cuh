@@ -18,6 +18,7 @@ struct GemmArgs {
   int64_t rows_per_batch = 0;  // 0 -> plain matrix
   int64_t batch_stride = 0;
   const float* W = nullptr;
+  const float* W_split = nullptr;  // [rna_tf32(W) | rna_tf32(W - hi)], 2*N*K floats (launch_split_tf32); tensor-core path only
   const float* bias = nullptr;
   float* C = nullptr;
   int64_t ldc = 0;
@@ -33,9 +34,11 @@ struct GemmArgs {
   int blocked_sum = 0;             // two-level summation over k tiles (used by the DFT rows)
 };
 cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches);
-// tcgen05 / TMEM / TMA path with 3xTF32 split accumulation (gemm_tc.cu).  Returns
+// tcgen05 / TMEM / TMA path with 3xTF32 split accumulation (gemm_tc.cu); needs g.W_split.  Returns
 // cudaErrorNotSupported when a tensor map cannot be encoded for this view.
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64_t* launches);
+// hl[0..n) = rna_tf32(w), hl[n..2n) = rna_tf32(w - hl[0..n)): the weight operand of launch_gemm_tc.
+cudaError_t launch_split_tf32(const float* w, float* hl, int64_t n, cudaStream_t s);
 
 // ---------------------------------------------------------------- normalisation / conv ---
 // y[m, :] = LayerNorm(x[m, :]) * gamma + beta over C channels (eps 1e-5, biased variance).

@@ -13,7 +13,7 @@ from .config import VelocityASRConfig, config_from_yaml, SCAN_MODES
 from .engine import VELOCITYASR
 from .frontend import compute_mel_spectrogram, SAMPLE_RATE, N_FFT, HOP_LENGTH, N_MELS
 from .ctc import ctc_greedy_decode, CTCDecoder, create_default_vocabulary, BLANK_TOKEN
-from .ops import selective_scan, selective_scan_fn, linear
+from .ops import selective_scan, selective_scan_fn, linear, split_tf32
 
 MAMBA_AVAILABLE = True  # scan_mode="mamba" is served by the in-tree scan kernel (ssm.py:20-26)
 
@@ -27,5 +27,5 @@ __all__ = [
     "__version__", "VELOCITYASR", "VelocityASRConfig", "config_from_yaml", "from_pretrained",
     "compute_mel_spectrogram", "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "N_MELS",
     "ctc_greedy_decode", "CTCDecoder", "create_default_vocabulary", "BLANK_TOKEN",
-    "selective_scan", "selective_scan_fn", "linear", "MAMBA_AVAILABLE", "SCAN_MODES",
+    "selective_scan", "selective_scan_fn", "linear", "split_tf32", "MAMBA_AVAILABLE", "SCAN_MODES",
 ]

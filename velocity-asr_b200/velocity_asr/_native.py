@@ -40,8 +40,9 @@ _SIGNATURES = {
     "vasr_transcribe_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "vasr_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                             c_int, c_void_p]),
-    "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
-                       c_int, c_void_p]),
+    "vasr_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                               c_int64, c_int, c_void_p]),
     "vasr_kernel_launches": (c_int64, [c_void_p]),
     "vasr_tc_launches": (c_int64, [c_void_p]),
     "vasr_workspace_bytes": (c_int64, [c_void_p]),

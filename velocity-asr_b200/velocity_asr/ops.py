@@ -60,11 +60,25 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 _ACT = {None: 0, "none": 0, "gelu": 1, "softplus": 2, "sigmoid": 3}
 
 
+def split_tf32(weight: torch.Tensor) -> torch.Tensor:
+    """(N, K) fp32 weight -> (2, N, K): [rna_tf32(w), rna_tf32(w - hi)], the operand format of the
+    tensor-core projection kernel.  Done once per weight matrix."""
+    if weight.device.type != "cuda":
+        raise RuntimeError("split_tf32 runs on CUDA only (no CPU fallback)")
+    weight = _f32c(weight)
+    out = torch.empty((2,) + tuple(weight.shape), device=weight.device, dtype=torch.float32)
+    with torch.cuda.device(weight.device):
+        _native.check(_native.lib().vasr_split_tf32(_native.ptr(weight), _native.ptr(out), weight.numel(),
+                                                    _stream(weight.device)))
+    return out
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-           activation: Optional[str] = None, tensor_cores: bool = False) -> torch.Tensor:
+           activation: Optional[str] = None, tensor_cores: bool = False,
+           weight_split: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.linear (+ optional activation) on (..., K) rows.  tensor_cores=False: CUDA-core fp32 kernel
-    (K % 16 == 0); True: tcgen05 3xTF32 kernel (K % 4 == 0) — the one the model's token-sized
-    projections run on."""
+    (K % 16 == 0); True: tcgen05 3xTF32 kernel (K % 4 == 0, N % 4 == 0) — the one the model's
+    token-sized projections run on; weight_split = split_tf32(weight) skips the per-call split."""
     if x.device.type != "cuda":
         raise RuntimeError("linear runs on CUDA only (no CPU fallback)")
     x, weight, bias = map(_f32c, (x, weight, bias))
@@ -75,8 +89,12 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     if x2.shape[0] > 0:
         lib = _native.lib()
         with torch.cuda.device(x.device):
-            fn = lib.vasr_linear_tc if tensor_cores else lib.vasr_linear
-            _native.check(fn(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(bias),
-                                          _native.ptr(out), N, x2.shape[0], K, N, _ACT[activation],
-                                          _stream(x.device)))
+            if tensor_cores:
+                _native.check(lib.vasr_linear_tc(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(weight_split),
+                                                 _native.ptr(bias), _native.ptr(out), N, x2.shape[0], K, N,
+                                                 _ACT[activation], _stream(x.device)))
+            else:
+                _native.check(lib.vasr_linear(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(bias),
+                                              _native.ptr(out), N, x2.shape[0], K, N, _ACT[activation],
+                                              _stream(x.device)))
     return out.reshape(*x.shape[:-1], N)
