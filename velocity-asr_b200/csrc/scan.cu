@@ -268,221 +268,333 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
 // ------------------------------------------------------------------------------------------
 // Fast path of the true recurrence (scan_mode sequential / mamba).
 //
-// ncu on the first version showed the scan is bound by shared-memory wavefronts, not by the FMA
-// pipe: a warp-wide 16-byte load runs in four 8-lane phases, a phase cannot broadcast across
-// phases, and B/C traffic per state update falls only with the number of rows a lane serves.
-// Here each lane keeps 8 states of TWO rows (16 state registers), so one B/C load feeds two
-// updates, and the B/C rows are stored permuted ([first 16 B of every lane | second 16 B of every
-// lane]) so that the 8 lanes of a phase read 128 contiguous bytes.  The staging threads also
-// pre-compute s = -dt*log2(e) and u = x*dt once per (t, row) instead of once per lane.
+// ncu on the previous version (8 states per lane, register-staged tiles): 115 issued instructions
+// per warp-step against 32 packed state operations — index arithmetic of the staging code, the
+// 8-lane transpose-reduce and the per-lane power set-up dominated, and the FMA pipe sat at 45 %.
+// This version is built to shrink everything that is not a state update:
+//   * 16 states per lane, two rows per lane (32 state registers as packed fp32x2): a row is owned by
+//     LPR = N/16 lanes, so the set-up cost per row-step (3 MUFU + 6 FMUL), the B/C loads (one
+//     16-byte load feeds eight state updates) and the reduction are amortised over twice the work;
+//   * B/C/x/dt/z tiles of 16 timesteps arrive by cp.async (LDGSTS) in their NATURAL layout, double
+//     buffered: no register staging, no permutation, no per-element address arithmetic.  Lane j
+//     reads the float4s j, j+LPR, j+2 LPR, j+3 LPR of a B/C row, i.e. the LPR lanes of a group read
+//     consecutive 16-byte pieces (conflict-free) and the lane's states are n = 4 (j + LPR m) + i;
+//   * structured A: p[n] = r^(n+1) with r = exp(-dt): the first quad is r^(4j+1) (1, r, r^2, r^3),
+//     every further quad is the previous one times r^(4 LPR) — three ex2 per row-step, all other
+//     powers are packed multiplies;
+//   * the partial dot products of four timesteps x two rows are transpose-reduced over the LPR
+//     lanes; the lane that ends up with a finished (t, row pair) applies the D skip and the
+//     silu(z) gate and stores the pair straight to global memory (8 bytes per lane, 64 contiguous
+//     bytes per timestep per warp).
 // ------------------------------------------------------------------------------------------
-constexpr int TC2 = 8;    // timesteps per staged chunk
+constexpr int TCH = 16;   // timesteps per staged chunk
 
-template <int LPR, int WARPS, bool STRUCT>
-__global__ void __launch_bounds__(WARPS * 32, 672 / (WARPS * 32)) scan_rows2_kernel(ScanArgs a) {
-  constexpr int N = LPR * SPL;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1 or 2)
+__global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
+  constexpr int N = LPR * 16;
   constexpr int GROUPS = 32 / LPR;             // lane groups per warp
-  constexpr int ROWS = WARPS * GROUPS * 2;     // rows per CTA
+  constexpr int ROWS = WARPS * GROUPS * RPL;   // rows per CTA
   constexpr int THREADS = WARPS * 32;
-  constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : 1);
-  constexpr int TPL = 8 >> NR;
-  constexpr int NBC = TC2 * (N / 4);           // float4 per chunk of B (and of C)
-  constexpr int NXD = TC2 * ROWS;              // elements per chunk of x (dt, z)
-  constexpr int PBC = (NBC + THREADS - 1) / THREADS;
-  constexpr int PXD = (NXD + THREADS - 1) / THREADS;
+  constexpr int NR = (LPR == 4) ? 2 : (LPR == 2 ? 1 : 0);
+  constexpr int NV = 4 * RPL;                  // partials per lane per block of 4 steps
+  constexpr int TPL = NV >> NR;                // finished (step, row) values per lane per 4 steps
+  constexpr int NF = N / 4, RF = ROWS / 4;     // float4 per B (C) row, per x (dt, z) row
+  constexpr int STAGE_FLOATS = TCH * (2 * N + 3 * ROWS);
 
-  // two buffers: chunk c+1 is committed into the other buffer while chunk c is being consumed,
-  // so one __syncthreads per chunk suffices
-  __shared__ __align__(16) float sB[2][TC2][N];
-  __shared__ __align__(16) float sC[2][TC2][N];
-  __shared__ __align__(16) float2 ssu[2][TC2][ROWS];  // (s, u)
-  __shared__ float sx[2][TC2][ROWS];
-  __shared__ float sz[2][TC2][ROWS];
-  __shared__ float sy[2][TC2][ROWS];
+  extern __shared__ __align__(16) float scan_smem[];
+  auto sB = [&](int st) { return scan_smem + st * STAGE_FLOATS; };
+  auto sC = [&](int st) { return scan_smem + st * STAGE_FLOATS + TCH * N; };
+  auto sX = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N; };
+  auto sDt = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N + TCH * ROWS; };
+  auto sZ = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N + 2 * TCH * ROWS; };
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane / LPR, j = lane % LPR;
-  const int rl0 = (warp * GROUPS + g) * 2;      // first of this lane's two rows (within the CTA)
-  const int n0 = j * SPL;
+  const int rl0 = (warp * GROUPS + g) * RPL;    // first of this lane's rows (within the CTA)
   const int d0 = blockIdx.x * ROWS;
   const int64_t b = blockIdx.y;
   const int64_t L = a.L;
   const bool gate = a.z != nullptr;
-  const int nchunks = (int)((L + TC2 - 1) / TC2);
+  const int nchunks = (int)((L + TCH - 1) / TCH);
 
-  float al2[SPL];
+  // per-lane exponent constants: exp(dt A[n]) = 2^(dt * A[n] * log2 e)
+  float al2[STRUCT ? 1 : 16];
+  if (!STRUCT) {
 #pragma unroll
-  for (int k = 0; k < SPL; ++k) al2[k] = a.A[n0 + k] * LOG2E;
-  const float n0p1 = (float)(n0 + 1);
-  float Dv[2] = {0.f, 0.f};
-  if (a.D) { Dv[0] = __ldg(a.D + d0 + rl0); Dv[1] = __ldg(a.D + d0 + rl0 + 1); }
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) al2[4 * m + i] = __ldg(a.A + 4 * (j + LPR * m) + i) * LOG2E;
+  }
+  const float c_r = -LOG2E;                          // r   = exp(-dt)
+  const float c_e = -LOG2E * (float)(4 * j + 1);     // e   = r^(4j+1)
+  const float c_q = -LOG2E * (float)(4 * LPR);       // rq  = r^(4 LPR)
+  float Dv[RPL];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) Dv[r] = a.D ? __ldg(a.D + d0 + rl0 + r) : 0.f;
 
-  State8 H0, H1;
+  u64 H[RPL][8];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) H0.v[k] = H1.v[k] = 0ull;
+  for (int r = 0; r < RPL; ++r)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) H[r][k] = 0ull;
 
-  // ---- software pipeline: the global loads of chunk c+1 are in flight while chunk c computes
-  float4 rb[PBC], rc[PBC];
-  float rx[PXD], rd[PXD], rz[PXD];
-  auto prefetch = [&](int c) {
-    const int64_t tc0 = (int64_t)c * TC2;
-    const int tcn = (int)((L - tc0) < TC2 ? (L - tc0) : TC2);
+  const float* gB = a.Bm + b * L * a.ldb;
+  const float* gC = a.Cm + b * L * a.ldc;
+  const float* gX = a.x + b * L * a.ldx + d0;
+  const float* gDt = a.dt + b * L * a.lddt + d0;
+  const float* gZ = gate ? a.z + b * L * a.ldz + d0 : nullptr;
+  float* gY = a.y + b * L * a.ldy + d0 + rl0;
+
+  auto issue = [&](int c) {          // always commits a group (an empty one past the last chunk)
+    const int st = c % 3;
+    const int64_t tc0 = (int64_t)c * TCH;
+    const int tcn = c >= nchunks ? 0 : (int)((L - tc0) < TCH ? (L - tc0) : TCH);
+    float* dB = sB(st); float* dC = sC(st); float* dX = sX(st); float* dD = sDt(st); float* dZ = sZ(st);
 #pragma unroll
-    for (int i = 0; i < PBC; ++i) {
+    for (int i = 0; i < (TCH * NF + THREADS - 1) / THREADS; ++i) {
       const int idx = tid + i * THREADS;
-      const int t = idx / (N / 4), f = idx % (N / 4);
-      rb[i] = rc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < NBC && t < tcn) {
-        const int64_t row = b * L + tc0 + t;
-        rb[i] = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
-        rc[i] = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
+      const int t = idx / NF, f = idx % NF;
+      if (idx < TCH * NF && t < tcn) {
+        cp_async16(dB + t * N + 4 * f, gB + (tc0 + t) * a.ldb + 4 * f);
+        cp_async16(dC + t * N + 4 * f, gC + (tc0 + t) * a.ldc + 4 * f);
       }
     }
 #pragma unroll
-    for (int i = 0; i < PXD; ++i) {
+    for (int i = 0; i < (TCH * RF + THREADS - 1) / THREADS; ++i) {
       const int idx = tid + i * THREADS;
-      const int t = idx / ROWS, r = idx % ROWS;
-      rx[i] = rd[i] = rz[i] = 0.f;
-      if (idx < NXD && t < tcn) {
-        const int64_t row = b * L + tc0 + t;
-        rx[i] = __ldg(a.x + row * a.ldx + d0 + r);
-        rd[i] = __ldg(a.dt + row * a.lddt + d0 + r);
-        if (gate) rz[i] = __ldg(a.z + row * a.ldz + d0 + r);
+      const int t = idx / RF, f = idx % RF;
+      if (idx < TCH * RF && t < tcn) {
+        cp_async16(dX + t * ROWS + 4 * f, gX + (tc0 + t) * a.ldx + 4 * f);
+        cp_async16(dD + t * ROWS + 4 * f, gDt + (tc0 + t) * a.lddt + 4 * f);
+        if (gate) cp_async16(dZ + t * ROWS + 4 * f, gZ + (tc0 + t) * a.ldz + 4 * f);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // one row, one timestep: advance the 16 states of Hr and return the partial <h, C>
+  auto row_step = [&](u64 (&Hr)[8], float dtv, float xv, const ulonglong2 (&bq)[4], const ulonglong2 (&cq)[4]) {
+    const float u = xv * dtv;
+    const u64 uu = pack2(u, u);
+    u64 Pa, Pb, rq2 = 0ull;
+    if (STRUCT) {
+      const float r = ex2_approx(dtv * c_r);
+      const float e = ex2_approx(dtv * c_e);
+      const float rq = ex2_approx(dtv * c_q);
+      const float r2 = r * r;
+      Pa = pack2(e, e * r);
+      Pb = mul2(Pa, pack2(r2, r2));
+      rq2 = pack2(rq, rq);
+    }
+    u64 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (!STRUCT) {
+        Pa = pack2(ex2_approx(dtv * al2[4 * m]), ex2_approx(dtv * al2[4 * m + 1]));
+        Pb = pack2(ex2_approx(dtv * al2[4 * m + 2]), ex2_approx(dtv * al2[4 * m + 3]));
+      }
+      Hr[2 * m] = fma2(Pa, Hr[2 * m], mul2(uu, bq[m].x));
+      Hr[2 * m + 1] = fma2(Pb, Hr[2 * m + 1], mul2(uu, bq[m].y));
+      if (m == 0) {
+        acc0 = mul2(Hr[0], cq[0].x);
+        acc1 = mul2(Hr[1], cq[0].y);
+      } else {
+        acc0 = fma2(Hr[2 * m], cq[m].x, acc0);
+        acc1 = fma2(Hr[2 * m + 1], cq[m].y, acc1);
+      }
+      if (STRUCT && m < 3) {
+        Pa = mul2(Pa, rq2);
+        Pb = mul2(Pb, rq2);
+      }
+    }
+    return hsum2(add2(acc0, acc1));
+  };
+
+  // operands of one timestep, fetched one step ahead of their use
+  struct Ops {
+    ulonglong2 bq[4], cq[4];
+    float dt[RPL], x[RPL];
+  };
+  auto load_ops = [&](Ops& o, const float* pB, const float* pC, const float* pX, const float* pD, int t) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      o.bq[m] = *reinterpret_cast<const ulonglong2*>(pB + t * N + 4 * LPR * m);
+      o.cq[m] = *reinterpret_cast<const ulonglong2*>(pC + t * N + 4 * LPR * m);
+    }
+    if (RPL == 2) {
+      const float2 d2 = *reinterpret_cast<const float2*>(pD + t * ROWS);
+      const float2 x2 = *reinterpret_cast<const float2*>(pX + t * ROWS);
+      o.dt[0] = d2.x; o.dt[RPL - 1] = d2.y; o.x[0] = x2.x; o.x[RPL - 1] = x2.y;
+    } else {
+      o.dt[0] = pD[t * ROWS]; o.x[0] = pX[t * ROWS];
+    }
+  };
+
+  // Reduce + D skip + gate + store of a block of four steps run one block LATE, interleaved with
+  // the state updates of the next block, so the shuffle and MUFU latencies hide behind FMA work.
+  // A lane finalises SPB = TPL / RPL steps (from step j*SPB of the block) of its RPL rows; their x
+  // and z are captured in registers when the block is computed, so nothing depends on the tile.
+  constexpr int SPB = TPL / RPL;
+  float ypv[NV], fx[TPL], fz[TPL];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ypv[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < TPL; ++i) fx[i] = fz[i] = 0.f;
+  float* fy = gY;
+  int fvalid = 0;          // how many of the SPB owned steps exist
+  auto finalize = [&]() {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int lane_bit = LPR >> (r + 1);
+      const int cnt = (NV / 2) >> r;
+      const bool hi = (j & lane_bit) != 0;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) {
+        const float mine = hi ? ypv[i + cnt] : ypv[i];
+        const float other = hi ? ypv[i] : ypv[i + cnt];
+        ypv[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
+      }
+    }
+#pragma unroll
+    for (int sp = 0; sp < SPB; ++sp) {
+      float y[RPL];
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) {
+        y[r] = fmaf(fx[sp * RPL + r], Dv[r], ypv[sp * RPL + r]);
+        if (gate) {   // y * silu(z) = y * z / (1 + 2^(-z log2 e))
+          const float zv = fz[sp * RPL + r];
+          float sg;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex2_approx(-zv * LOG2E)));
+          y[r] *= zv * sg;
+        }
+      }
+      if (sp < fvalid) {
+        if (RPL == 2) *reinterpret_cast<float2*>(fy + sp * a.ldy) = make_float2(y[0], y[RPL - 1]);
+        else fy[sp * a.ldy] = y[0];
       }
     }
   };
-  // B/C rows are stored permuted: float4 f = 2*jj + c of a row lands at slot c*LPR + jj, so the
-  // 8 lanes of a 16-byte load phase read 128 contiguous bytes
-  auto commit = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < PBC; ++i) {
-      const int idx = tid + i * THREADS;
-      if (idx < NBC) {
-        const int t = idx / (N / 4), f = idx % (N / 4);
-        const int slot = (f & 1) * LPR + (f >> 1);
-        *reinterpret_cast<float4*>(&sB[buf][t][4 * slot]) = rb[i];
-        *reinterpret_cast<float4*>(&sC[buf][t][4 * slot]) = rc[i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < PXD; ++i) {
-      const int idx = tid + i * THREADS;
-      if (idx < NXD) {
-        const int t = idx / ROWS, r = idx % ROWS;
-        ssu[buf][t][r] = make_float2(STRUCT ? -rd[i] * LOG2E : rd[i], rx[i] * rd[i]);
-        sx[buf][t][r] = rx[i];
-        sz[buf][t][r] = rz[i];
-      }
-    }
-  };
 
-  prefetch(0);
-  commit(0);
-  __syncthreads();
-
+  constexpr int NST = 3;   // tile stages: chunk c+2 is in flight while chunk c is consumed
+  issue(0);
+  issue(1);
   for (int c = 0; c < nchunks; ++c) {
-    const int64_t tc0 = (int64_t)c * TC2;
-    const int tcn = (int)((L - tc0) < TC2 ? (L - tc0) : TC2);
-    const int buf = c & 1;
-    if (c + 1 < nchunks) prefetch(c + 1);
+    const int st = c % NST;
+    const int64_t tc0 = (int64_t)c * TCH;
+    const int tcn = (int)((L - tc0) < TCH ? (L - tc0) : TCH);
+    cp_async_wait<1>();                   // every chunk but the newest has landed (for this thread)
+    __syncthreads();                      // ... for every thread; and everyone is done with chunk c-1
+    issue(c + 2);                         // refills the stage of chunk c-1
+    const float* pB = sB(st) + 4 * j;
+    const float* pC = sC(st) + 4 * j;
+    const float* pX = sX(st) + rl0;
+    const float* pD = sDt(st) + rl0;
+    const float* pZ = sZ(st) + rl0;
 
+    Ops cur;
+    load_ops(cur, pB, pC, pX, pD, 0);
 #pragma unroll 1
-    for (int g4 = 0; g4 < TC2; g4 += 4) {
-      float yp[8];   // index 2*i + r : step i, row r
+    for (int g4 = 0; g4 < TCH; g4 += 4) {
+      if (g4 >= tcn) break;
+      float yp[NV];   // index RPL*i + r : step i, row r
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int t = g4 + i;
-        const float4 su = *reinterpret_cast<const float4*>(&ssu[buf][t][rl0]);   // (s0,u0,s1,u1)
-        const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(&sB[buf][t][4 * j]);
-        const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(&sB[buf][t][4 * (LPR + j)]);
-        const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[buf][t][4 * j]);
-        const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[buf][t][4 * (LPR + j)]);
-        State8 p;
-        u64 uu, acc, acc2;
-        if (STRUCT) powers_structured(su.x, n0p1, p); else powers_generic(su.x, al2, p);
-        uu = pack2(su.y, su.y);
-        H0.v[0] = fma2(p.v[0], H0.v[0], mul2(uu, b01.x));
-        H0.v[1] = fma2(p.v[1], H0.v[1], mul2(uu, b01.y));
-        H0.v[2] = fma2(p.v[2], H0.v[2], mul2(uu, b23.x));
-        H0.v[3] = fma2(p.v[3], H0.v[3], mul2(uu, b23.y));
-        acc = fma2(H0.v[1], c01.y, mul2(H0.v[0], c01.x));
-        acc2 = fma2(H0.v[3], c23.y, mul2(H0.v[2], c23.x));
-        yp[2 * i] = hsum2(add2(acc, acc2));
-        if (STRUCT) powers_structured(su.z, n0p1, p); else powers_generic(su.z, al2, p);
-        uu = pack2(su.w, su.w);
-        H1.v[0] = fma2(p.v[0], H1.v[0], mul2(uu, b01.x));
-        H1.v[1] = fma2(p.v[1], H1.v[1], mul2(uu, b01.y));
-        H1.v[2] = fma2(p.v[2], H1.v[2], mul2(uu, b23.x));
-        H1.v[3] = fma2(p.v[3], H1.v[3], mul2(uu, b23.y));
-        acc = fma2(H1.v[1], c01.y, mul2(H1.v[0], c01.x));
-        acc2 = fma2(H1.v[3], c23.y, mul2(H1.v[2], c23.x));
-        yp[2 * i + 1] = hsum2(add2(acc, acc2));
+        Ops nxt;
+        load_ops(nxt, pB, pC, pX, pD, t + 1 < TCH ? t + 1 : TCH - 1);
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) yp[RPL * i + r] = row_step(H[r], cur.dt[r], cur.x[r], cur.bq, cur.cq);
+        cur = nxt;
       }
-      // transpose-reduce the 8 partials over the LPR lanes of the group
+      // x and z of the values this lane will finalise one block from now
+      float nfx[TPL], nfz[TPL];
+      const int s0 = g4 + j * SPB;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const int lane_bit = LPR >> (r + 1);
-        const int cnt = 4 >> r;
-        const bool hi = (j & lane_bit) != 0;
-#pragma unroll
-        for (int i = 0; i < cnt; ++i) {
-          const float mine = hi ? yp[i + cnt] : yp[i];
-          const float other = hi ? yp[i] : yp[i + cnt];
-          yp[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
+      for (int sp = 0; sp < SPB; ++sp) {
+        if (RPL == 2) {
+          const float2 x2 = *reinterpret_cast<const float2*>(pX + (s0 + sp) * ROWS);
+          const float2 z2 = gate ? *reinterpret_cast<const float2*>(pZ + (s0 + sp) * ROWS) : make_float2(0.f, 0.f);
+          nfx[sp * RPL] = x2.x; nfx[sp * RPL + RPL - 1] = x2.y;
+          nfz[sp * RPL] = z2.x; nfz[sp * RPL + RPL - 1] = z2.y;
+        } else {
+          nfx[sp] = pX[(s0 + sp) * ROWS];
+          nfz[sp] = gate ? pZ[(s0 + sp) * ROWS] : 0.f;
         }
       }
-      // lane j owns values v = j*TPL + i: step v >> 1, row v & 1
+      finalize();                          // the PREVIOUS block
 #pragma unroll
-      for (int i = 0; i < TPL; ++i) {
-        const int v = j * TPL + i;
-        const int t = g4 + (v >> 1), rr = v & 1;
-        float yv = yp[i] + sx[buf][t][rl0 + rr] * (rr ? Dv[1] : Dv[0]);
-        if (gate) {
-          const float zv = sz[buf][t][rl0 + rr];
-          yv *= zv / (1.0f + __expf(-zv));
-        }
-        sy[buf][t][rl0 + rr] = yv;
-      }
-    }
-    if (c + 1 < nchunks) commit(buf ^ 1);   // other buffer: last read during chunk c-1, before the previous barrier
-    __syncthreads();                        // sy[buf] complete, chunk c+1 visible
-    for (int idx = tid; idx < tcn * ROWS; idx += THREADS) {
-      const int t = idx / ROWS, r = idx % ROWS;
-      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[buf][t][r];   // sy[buf] is next written during chunk c+2
+      for (int i = 0; i < NV; ++i) ypv[i] = yp[i];
+#pragma unroll
+      for (int i = 0; i < TPL; ++i) { fx[i] = nfx[i]; fz[i] = nfz[i]; }
+      fy = gY + (tc0 + s0) * a.ldy;
+      fvalid = tcn - s0;
     }
   }
+  finalize();
 }
 
-template <int LPR, int WARPS>
-cudaError_t launch_rows2(const ScanArgs& a, cudaStream_t s) {
-  constexpr int ROWS = WARPS * (32 / LPR) * 2;
+template <int LPR, int WARPS, int RPL>
+cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
+  constexpr int N = LPR * 16;
+  constexpr int ROWS = WARPS * (32 / LPR) * RPL;
+  constexpr size_t SMEM = (size_t)3 * TCH * (2 * N + 3 * ROWS) * sizeof(float);
   dim3 grid((unsigned)(a.Di / ROWS), (unsigned)a.B);
-  if (a.structured_a) scan_rows2_kernel<LPR, WARPS, true><<<grid, WARPS * 32, 0, s>>>(a);
-  else scan_rows2_kernel<LPR, WARPS, false><<<grid, WARPS * 32, 0, s>>>(a);
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  auto go = [&](auto kernel) {
+    if (SMEM > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e == cudaSuccess) kernel<<<grid, WARPS * 32, SMEM, s>>>(a);
+  };
+  if (a.structured_a) go(scan_seq_kernel<LPR, WARPS, RPL, true>);
+  else go(scan_seq_kernel<LPR, WARPS, RPL, false>);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// picks the CTA width: 3 warps (24 rows at N = 64) tiles 384 channels x 64 utterances onto
-// 148 SMs almost evenly (1024 CTAs, 6.9 per SM); other widths are fallbacks for other Di.
+// picks the CTA shape: rows per CTA must divide Di.  VASR_SCAN_RPL=1|2 overrides rows per lane.
 template <int LPR>
 cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
-  constexpr int RPW = (32 / LPR) * 2;
-  if (a.Di % (3 * RPW) == 0) return launch_rows2<LPR, 3>(a, s);
-  if (a.Di % (4 * RPW) == 0) return launch_rows2<LPR, 4>(a, s);
-  if (a.Di % (2 * RPW) == 0) return launch_rows2<LPR, 2>(a, s);
-  if (a.Di % RPW == 0) return launch_rows2<LPR, 1>(a, s);
+  constexpr int G = 32 / LPR;
+  // cp.async moves 16-byte pieces: every row start must be 16-byte aligned
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((a.ldx & 3) || (a.lddt & 3) || (a.ldy & 1) || !al16(a.x) || !al16(a.dt) || (a.z && ((a.ldz & 3) || !al16(a.z))) ||
+      (reinterpret_cast<uintptr_t>(a.y) & 7))
+    return cudaErrorInvalidValue;
+  static const int rpl_env = [] { const char* e = getenv("VASR_SCAN_RPL"); return e ? atoi(e) : 0; }();
+  const int rpl = rpl_env == 1 || rpl_env == 2 ? rpl_env : 2;
+  static const int warps_env = [] { const char* e = getenv("VASR_SCAN_WARPS"); return e ? atoi(e) : 0; }();
+  if (rpl == 2) {
+    // four warps = one warp of the CTA per SM sub-partition: the warps of a CTA then advance at the
+    // same rate and the per-chunk barrier costs nothing (measured 0.320 ms vs 0.356 ms with three)
+    if (LPR == 4 && warps_env != 3 && a.Di % (4 * G * 2) == 0) return launch_seq<LPR, 4, 2>(a, s);
+    if (LPR == 4 && a.Di % (3 * G * 2) == 0) return launch_seq<LPR, 3, 2>(a, s);
+    if (a.Di % (2 * G * 2) == 0 && 2 * G * 2 <= 128) return launch_seq<LPR, 2, 2>(a, s);
+    if (a.Di % (G * 2) == 0) return launch_seq<LPR, 1, 2>(a, s);
+  }
+  if (LPR == 4 && a.Di % (6 * G) == 0) return launch_seq<LPR, 6, 1>(a, s);
+  if (LPR == 4 && a.Di % (3 * G) == 0) return launch_seq<LPR, 3, 1>(a, s);
+  if (a.Di % (4 * G) == 0 && 4 * G <= 128) return launch_seq<LPR, 4, 1>(a, s);
+  if (a.Di % (2 * G) == 0 && 2 * G <= 128) return launch_seq<LPR, 2, 1>(a, s);
+  if (a.Di % G == 0) return launch_seq<LPR, 1, 1>(a, s);
   return cudaErrorInvalidValue;
 }
 
-template <int LPR>
+template <int LPR8>   // LPR8 = N / 8: lanes per row of the quirk kernel
 cudaError_t launch_lpr(const ScanArgs& a, cudaStream_t s) {
-  constexpr int ROWS = SCAN_THREADS / LPR;
+  if (!a.parallel_quirk) return launch_recurrence<LPR8 / 2>(a, s);
+  constexpr int ROWS = SCAN_THREADS / LPR8;
   if (a.Di % ROWS != 0) return cudaErrorInvalidValue;
   dim3 grid((unsigned)(a.Di / ROWS), (unsigned)a.B);
-  if (!a.parallel_quirk) return launch_recurrence<LPR>(a, s);
-  if (a.structured_a) scan_quirk_kernel<LPR, true><<<grid, SCAN_THREADS, 0, s>>>(a);
-  else scan_quirk_kernel<LPR, false><<<grid, SCAN_THREADS, 0, s>>>(a);
+  if (a.structured_a) scan_quirk_kernel<LPR8, true><<<grid, SCAN_THREADS, 0, s>>>(a);
+  else scan_quirk_kernel<LPR8, false><<<grid, SCAN_THREADS, 0, s>>>(a);
   return cudaGetLastError();
 }
 
