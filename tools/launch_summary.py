@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list of bench.py: per-kernel
-share of ONE timed step (the launches between two reflect_pad kernels).  Usage:
+share of ONE timed step (the launches between two front-end kernels).  Usage:
     python tools/launch_summary.py gpurun_out/launches.csv [step_index] > profiles/rNN_launches.md"""
 import collections, csv, re, sys
 
@@ -8,7 +8,7 @@ def main(path, step=3):
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    starts = [i for i, n in enumerate(names) if "reflect_pad" in n]
+    starts = [i for i, n in enumerate(names) if "mel_fft_kernel" in n or "reflect_pad" in n]
     i0 = starts[step]
     i1 = starts[step + 1] if step + 1 < len(starts) else len(rows)
     agg, tot = collections.OrderedDict(), 0.0

@@ -84,7 +84,10 @@ struct vasr_handle {
   float *w_q = nullptr, *b_q = nullptr, *w_kv = nullptr, *b_kv = nullptr, *w_o = nullptr, *b_o = nullptr;
   float *w_f3 = nullptr, *b_f3 = nullptr, *w_fo = nullptr, *b_fo = nullptr;
   float *ctc_g = nullptr, *ctc_b = nullptr, *w_ctc = nullptr, *b_ctc = nullptr;
-  float* dft_w = nullptr;
+  float* dft_w = nullptr;    // [hann*cos | hann*sin] table of the dense-DFT route (VASR_MEL=dft)
+  float* win = nullptr;      // analysis window (400)
+  float* tw400 = nullptr;    // W400^m = (cos, -sin)(2 pi m / 400)
+  int mel_dft = 0;           // VASR_MEL=dft: first-version route (DFT as a strided projection), kept for A/B runs
   int *fb_lo = nullptr, *fb_off = nullptr;
   float* fb_w = nullptr;
 
@@ -139,6 +142,7 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
 
 struct Work {
   float *xp, *spec, *raw, *mean, *rstd, *melpad;
+  double* part;
   float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
   float *ga, *gb, *g2, *g2n, *kv;
   float* logits;
@@ -155,8 +159,11 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   const int nmax = h->cfg.ssm_state_dim > h->cfg.global_ssm_state_dim ? h->cfg.ssm_state_dim
                                                                       : h->cfg.global_ssm_state_dim;
   if (need_mel) {
-    t.xp = a.take<float>(q.B * q.ldp);
-    t.spec = a.take<float>(q.B * q.T * SPEC_LD);
+    if (h->mel_dft) {
+      t.xp = a.take<float>(q.B * q.ldp);
+      t.spec = a.take<float>(q.B * q.T * SPEC_LD);
+    }
+    t.part = a.take<double>(q.B * mel_fft_blocks(q.T) * q.n_mels * 2);
     t.raw = a.take<float>(q.B * q.T * q.n_mels);
     t.mean = a.take<float>(q.B * q.n_mels);
     t.rstd = a.take<float>(q.B * q.n_mels);
@@ -339,6 +346,14 @@ int pack_frontend_impl(vasr_handle* h) {
       tab[(size_t)(N_FREQ + k) * N_FFT + n] = (float)((double)win[n] * sin(ang));
     }
   RET(upload(h, tab.data(), tab.size(), &h->dft_w));
+  RET(upload(h, win.data(), win.size(), &h->win));
+  std::vector<float> tw((size_t)2 * N_FFT);
+  for (int m = 0; m < N_FFT; ++m) {
+    const double ang = 2.0 * M_PI * (double)m / (double)N_FFT;
+    tw[2 * m] = (float)cos(ang);
+    tw[2 * m + 1] = (float)(-sin(ang));
+  }
+  RET(upload(h, tw.data(), tw.size(), &h->tw400));
   std::vector<int> lo(n_mels), off(n_mels + 1, 0);
   std::vector<float> wts;
   for (int j = 0; j < n_mels; ++j) {
@@ -530,6 +545,12 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
 
 // PCM (device) -> k.raw (+ mean/rstd when normalize)
 int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int normalize, cudaStream_t s) {
+  if (!h->mel_dft) {
+    KL(launch_mel_fft(pcm, k.raw, normalize ? k.part : nullptr, q.B, q.S, q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w,
+                      h->win, h->tw400, s, &h->launches));
+    if (normalize) KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches));
+    return VASR_OK;
+  }
   KL(launch_reflect_pad(pcm, k.xp, q.B, q.S, PAD, q.ldp, s, &h->launches));
   GemmArgs g;
   g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
@@ -610,6 +631,7 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   if (const char* ev = getenv("VASR_GEMM")) h->use_tc = strcmp(ev, "simt") != 0;
   if (const char* ev = getenv("VASR_DFT")) h->dft_tc = strcmp(ev, "tc") == 0;
+  if (const char* ev = getenv("VASR_MEL")) h->mel_dft = strcmp(ev, "dft") == 0;
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));

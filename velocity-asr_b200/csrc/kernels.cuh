@@ -68,6 +68,17 @@ struct ScanArgs {
 cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* launches);
 
 // ---------------------------------------------------------------- log-mel front end -----
+// One pass PCM (B, S) -> raw (B, T, n_mels) = log(mel power + 1e-10): reflect padding by index, window,
+// 400-point FFT, power, band-sparse filterbank (weights fb_w[fb_off[j] .. fb_off[j+1]) on frequency bins
+// fb_lo[j] ...), log.  win: 400 taps; tw: 400 x (cos, -sin)(2 pi m / 400).  part (B, mel_fft_blocks(T),
+// n_mels, 2) doubles receives per-CTA (mean, M2) partials for launch_mel_stats_combine (NULL to skip).
+int64_t mel_fft_blocks(int64_t T);
+cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B, int64_t S, int64_t T, int n_mels,
+                           const int* fb_lo, const int* fb_off, const float* fb_w, const float* win,
+                           const float* tw, cudaStream_t s, int64_t* launches);
+// per (b, j): mean and 1/(unbiased std + 1e-10) over the T frames, from the partials above.
+cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
+                                     cudaStream_t s, int64_t* launches);
 // xp[b, i] = pcm[b, reflect(i - pad)], i in [0, S + 2 pad); row stride ldp.
 cudaError_t launch_reflect_pad(const float* pcm, float* xp, int64_t B, int64_t S, int pad, int64_t ldp,
                                cudaStream_t s, int64_t* launches);
