@@ -274,6 +274,21 @@ def test_transcribe_paths_agree_and_shard(va):
     assert oracle == dev[:2]
 
 
+def test_transcribe_batches_pipeline(va):
+    """The pipelined stream API returns exactly what one transcribe() call per batch returns,
+    including when the batch shape changes mid-stream."""
+    m = make_model(va, "sequential", amp=True)
+    batches = [FU.synth_audio(4, 32000, seed=21).pin_memory(), FU.synth_audio(4, 32000, seed=22).pin_memory(),
+               FU.synth_audio(2, 48000, seed=23).pin_memory(), FU.synth_audio(4, 32000, seed=24)]
+    streamed = list(m.transcribe_batches(iter(batches)))
+    assert len(streamed) == len(batches)
+    for got, a in zip(streamed, batches):
+        assert got == m.transcribe(a.cuda())
+    assert list(m.transcribe_batches(iter([]))) == []
+    with pytest.raises(RuntimeError):
+        list(m.transcribe_batches(iter([batches[0].cuda()])))
+
+
 def test_long_form_needs_longer_table(va):
     m = make_model(va, "sequential")
     mel = torch.randn(1, 10003, 80, device="cuda")      # 5002 tokens > pe_time rows (model.py:87,125)

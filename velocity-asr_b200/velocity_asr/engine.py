@@ -3,7 +3,7 @@ object: parameters live in a torch module tree with the reference's state_dict k
 runs entirely in libvasr.so (hand-written sm_100a kernels) through the C ABI."""
 import ctypes
 import os
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, Iterable, Iterator, List, Optional, Tuple, Union
 
 import torch
 import torch.nn as nn
@@ -15,6 +15,12 @@ from .params import build_parameter_tree, reference_init_, time_table
 
 def _stream_ptr(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _token_lists(tokens: torch.Tensor, lens: torch.Tensor) -> List[List[int]]:
+    """(B, L) left-packed int32 ids + (B,) counts (host tensors) -> ragged Python lists."""
+    tok = tokens.numpy()
+    return [tok[b, :n].tolist() for b, n in enumerate(lens.tolist())]
 
 
 class _Engine:
@@ -92,8 +98,18 @@ class VELOCITYASR(nn.Module):
             self._engines[idx] = eng
         from .frontend import frontend_tables
         fb, win = frontend_tables(self.config.mel_bins)
-        eng.sync_weights(self.state_dict(), {"frontend.mel_filterbank": fb, "frontend.window": win})
+        # same keys and order as state_dict(), without the detach/copy work of building one per call
+        state = dict(self.named_parameters())
+        state.update({k: v for k, v in self.named_buffers() if k.split(".")[-1] not in self._non_persistent})
+        eng.sync_weights(state, {"frontend.mel_filterbank": fb, "frontend.window": win})
         return eng
+
+    @property
+    def _non_persistent(self):
+        names = set()
+        for m in self.modules():
+            names |= set(getattr(m, "_non_persistent_buffers_set", ()))
+        return names
 
     def _check_input(self, x: torch.Tensor, what: str) -> torch.Tensor:
         if not isinstance(x, torch.Tensor):
@@ -150,6 +166,7 @@ class VELOCITYASR(nn.Module):
             lens = torch.empty(B, dtype=torch.int32, pin_memory=True)
             _native.check(eng.lib.vasr_transcribe_host(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
                                                        _native.ptr(lens)))
+            return _token_lists(tokens, lens)
         else:
             pcm = self._check_input(audio, "audio")
             tokens = torch.empty(B, L, dtype=torch.int32, device=pcm.device)
@@ -157,7 +174,61 @@ class VELOCITYASR(nn.Module):
             _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
                                                   _native.ptr(lens), _stream_ptr(pcm.device)))
             tokens, lens = tokens.cpu(), lens.cpu()
-        return [tokens[b, : int(lens[b])].tolist() for b in range(B)]
+        return _token_lists(tokens, lens)
+
+    @torch.no_grad()
+    def transcribe_batches(self, batches: Iterable[torch.Tensor]) -> Iterator[List[List[int]]]:
+        """transcribe() over a stream of host batches, pipelined: while the kernels of batch i run,
+        batch i+1 is copied host->device on a second stream and the token ids of batch i-1 are copied
+        back and turned into lists.  Yields one List[List[int]] per input batch, in order; results
+        are identical to calling transcribe() on each batch.  Batches are (B, S) float32 CPU
+        tensors (pin them for full PCIe speed); shapes may change from batch to batch."""
+        dev = self._device()
+        eng = self._engine(dev)
+        comp = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        slots = [dict(pcm=None, tok=None, lens=None, tok_h=None, lens_h=None,
+                      h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        pending = None          # (slot, B) of the batch whose results are still on the device
+        i = 0
+        for audio in batches:
+            if audio.device.type != "cpu":
+                raise RuntimeError("transcribe_batches takes host batches; use transcribe() for CUDA tensors")
+            if audio.dim() == 1:
+                audio = audio.unsqueeze(0)
+            audio = audio.to(torch.float32).contiguous()
+            B, S = audio.shape
+            L = self.get_output_length(1 + S // 160)
+            sl = slots[i % 2]
+            if sl["pcm"] is None or sl["pcm"].shape != (B, S):
+                sl["pcm"] = torch.empty(B, S, device=dev, dtype=torch.float32)
+                sl["tok"] = torch.empty(B, L, device=dev, dtype=torch.int32)
+                sl["lens"] = torch.empty(B, device=dev, dtype=torch.int32)
+                sl["tok_h"] = torch.empty(B, L, dtype=torch.int32, pin_memory=True)
+                sl["lens_h"] = torch.empty(B, dtype=torch.int32, pin_memory=True)
+                copy.wait_stream(comp)          # a re-allocated buffer may still be in use by queued kernels
+            with torch.cuda.stream(copy):
+                copy.wait_event(sl["free"])      # the kernels that last read this slot's PCM are done
+                sl["pcm"].copy_(audio, non_blocking=True)
+                sl["h2d"].record(copy)
+            comp.wait_event(sl["h2d"])
+            _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(sl["pcm"]), B, S, _native.ptr(sl["tok"]),
+                                                  _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
+            sl["free"].record(comp)
+            sl["tok_h"].copy_(sl["tok"], non_blocking=True)
+            sl["lens_h"].copy_(sl["lens"], non_blocking=True)
+            sl["done"].record(comp)
+            if pending is not None:
+                yield self._collect(pending)
+            pending = sl
+            i += 1
+        if pending is not None:
+            yield self._collect(pending)
+
+    @staticmethod
+    def _collect(sl) -> List[List[int]]:
+        sl["done"].synchronize()
+        return _token_lists(sl["tok_h"], sl["lens_h"])
 
     def extend_positional_table(self, rows: int) -> None:
         """Regenerate pe_time with `rows` rows by the formula of model.py:94-100.  The reference
