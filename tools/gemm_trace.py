@@ -1,0 +1,28 @@
+"""Pipeline trace of the tensor-core projection kernel (VASR_GEMM=tc1: single-CTA version): clock64 stamps of CTA 0 at
+TMA issue (P), converter sees the tile (C0), converter done (C1), MMA warp released (M0), MMAs issued (M1)."""
+import os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "velocity-asr_b200"))
+import torch
+import velocity_asr as va
+from velocity_asr import _native
+lib = _native.lib()
+lib._FuncPtr  # noqa
+fn = lib.vasr_debug_gemm_trace
+fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p]
+M, K, N = 48064, 192, 768
+x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
+ws = va.split_tf32(w)
+for _ in range(3): va.linear(x, w, None, tensor_cores=True, weight_split=ws)
+buf = torch.zeros(5 * 128, dtype=torch.int64, device="cuda")
+fn(ctypes.c_void_p(buf.data_ptr()))
+va.linear(x, w, None, tensor_cores=True, weight_split=ws)
+torch.cuda.synchronize()
+fn(None)
+t = buf.cpu().view(5, 128)
+base = int(t[0, 0])
+print("stage   P(issue)  C0(full)  C1(conv)  M0(go)  M1(issued) | tma=C0-P conv=C1-C0 wake=M0-C1 issue=M1-M0 period=P[i]-P[i-1]")
+for i in range(40):
+    P, C0, C1, M0, M1 = [int(t[r, i]) - base for r in range(5)]
+    prev = int(t[0, i - 1]) - base if i else 0
+    print(f"{i:3d} {P:9d} {C0:9d} {C1:9d} {M0:8d} {M1:9d} | {C0-P:6d} {C1-C0:6d} {M0-C1:6d} {M1-M0:6d} {P-prev:6d}")

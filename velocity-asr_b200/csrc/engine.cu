@@ -960,6 +960,13 @@ int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const fl
   return VASR_OK;
 }
 
+/* debug hook (not in vasr.h): device buffer of 5 x 128 int64 that CTA 0 of the next tensor-core
+ * projection launches fills with clock64 at its pipeline events; NULL switches it off. */
+int vasr_debug_gemm_trace(long long* dev_buf) {
+  g_trace = dev_buf;
+  return VASR_OK;
+}
+
 int64_t vasr_tc_launches(const vasr_handle* h) { return h ? h->tc_launches : 0; }
 int64_t vasr_kernel_launches(const vasr_handle* h) { return h ? h->launches : 0; }
 int64_t vasr_workspace_bytes(const vasr_handle* h) { return h ? (int64_t)h->ws.bytes : 0; }

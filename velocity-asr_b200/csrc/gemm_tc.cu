@@ -31,6 +31,9 @@
 // with a 3-D tensor map (k, row-in-batch, batch); M tiles never straddle a batch.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -71,21 +74,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// The clock is only started when the first probe fails: in steady state the barrier is already
+// complete and the wait costs one try_wait (the MMA warp's per-stage bookkeeping is on the
+// critical path of the tensor pipe).
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
+  while (!mbar_try(bar, parity))
     if (clock64() - t0 > 4000000000LL) __trap();
-  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -118,6 +128,15 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// true in exactly one lane of a converged warp.  The MMA operands are computed OUTSIDE the elected branch,
+// from warp-uniform values only, so they sit in uniform registers: with operands derived from a
+// per-thread value (e.g. the TMEM base read back from shared memory) ptxas wraps every UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop, ~85 clocks of dependent latency per MMA (round-1 trace).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -176,7 +195,12 @@ struct TcArgs {
   const float* pe_time;
   const float* pe_freq;
   int pe_half;
+  long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
 };
+constexpr int TRACE_SLOTS = 128;
+__device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
+  if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
+}
 
 template <int ACT, bool PE, bool RESID>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -213,35 +237,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // the whole TMEM (512 columns) is allocated, so the base can only be 0: using the literal keeps every
+  // TMEM address warp-uniform for the compiler (see elect_one)
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = (int)(tile % g.n_tiles);
-        const int64_t mt = tile / g.n_tiles;
-        const int batch = (int)(mt / g.m_tiles_per_batch);
-        const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
-          const uint32_t sb = stage0 + stage * STAGE_BYTES;
+    // (whole warp runs the loop so that coordinates and addresses stay warp-uniform; one lane issues)
+    uint32_t stage = 0, phase = 0;
+    int tr_i = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % g.n_tiles);
+      const int64_t mt = tile / g.n_tiles;
+      const int batch = (int)(mt / g.m_tiles_per_batch);
+      const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+        if (lane == 0) trace_ev(g, 0, tr_i);
+        ++tr_i;
+        const uint32_t sb = stage0 + stage * STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(BAR(B_FULL + stage), 3 * TILE_BYTES);
           tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(B_FULL + stage));
           tma_load_2d(sb + TILE_BYTES, &tmWh, kb * TBK, nt * TBN, BAR(B_FULL + stage));
           tma_load_2d(sb + 2 * TILE_BYTES, &tmWl, kb * TBK, nt * TBN, BAR(B_FULL + stage));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t stage = 0, phase = 0;
     int64_t it = 0;
+    int tr_i = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = (int)(tile % g.n_tiles);
       // columns of this tile that exist, rounded up to the MMA's N granularity (16)
@@ -256,10 +289,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(BAR(B_FULL + stage), phase);    // W tiles landed (async proxy)
         mbar_wait(BAR(B_CONV + stage), phase);    // A hi/lo are in TMEM
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sb = stage0 + stage * STAGE_BYTES;
-          const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + 2 * TILE_BYTES);
-          const uint32_t a_hi = tmem_base + TMEM_A0 + stage * 64, a_lo = a_hi + 32;
+        if (lane == 0) trace_ev(g, 3, tr_i);
+        const uint32_t sb = stage0 + stage * STAGE_BYTES;
+        const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + 2 * TILE_BYTES);
+        const uint32_t a_hi = tmem_base + TMEM_A0 + stage * 64, a_lo = a_hi + 32;
+        if (elect_one()) {
 #pragma unroll
           for (int k4 = 0; k4 < TBK / 8; ++k4) {
             const uint64_t adv = (uint64_t)(k4 * 2);   // 8 tf32 = 32 bytes = 2 x 16-byte units
@@ -269,7 +303,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           umma_commit(BAR(B_EMPTY + stage));
           if (kb == nkb - 1) umma_commit(BAR(B_TFULL + acc));
+          trace_ev(g, 4, tr_i);
         }
+        ++tr_i;
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -283,9 +319,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
     uint32_t stage = 0, phase = 0;
+    int tr_i = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(B_FULL + stage), phase);
+        if (threadIdx.x == 64) trace_ev(g, 1, tr_i);
         const uint8_t* arow = smem + stage * STAGE_BYTES + row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -304,6 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(BAR(B_CONV + stage));
+        if (threadIdx.x == 64) trace_ev(g, 2, tr_i);
+        ++tr_i;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -393,6 +433,324 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =============================================================================================
+// CTA-pair version (cta_group::2).  ncu on the single-CTA kernel above: the tensor pipe is 48 % busy
+// and shared memory 77 % — per 32-deep k-step a CTA moves 896 wavefronts (TMA writes of A and of
+// both W tiles, the converter's read of A, three MMA reads of W) against 768 clocks of MMA.  Two CTAs
+// of a cluster (one TPC) therefore share a 256 x 128 tile: each holds its own 128 rows of A (in its
+// own TMEM) and HALF of the W tile; one tcgen05.mma.cta_group::2 issued by the leader drives both
+// tensor cores, and each SM's shared memory sees 576 wavefronts per k-step (A in + A read + half of W
+// in + half of the W reads).  Barriers: the W-full, conversion-done and accumulator-empty barriers
+// live in the leader and are signalled remotely by the peer; stage-empty and accumulator-full are
+// multicast to both CTAs by tcgen05.commit.
+// =============================================================================================
+constexpr int P_STAGE_BYTES = 2 * TILE_BYTES;                         // A (16 KB) | W_hi half (8 KB) | W_lo half (8 KB)
+constexpr int P_STAGES = 4;
+constexpr int P_BAR_OFFSET = P_STAGES * P_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int P_SMEM_BYTES = P_BAR_OFFSET + 256 + 1024;
+// barrier indices (per CTA; the leader's copies of WFULL / CONV / TEMPTY are the ones in use)
+constexpr int PB_AFULL = 0, PB_WFULL = P_STAGES, PB_CONV = 2 * P_STAGES, PB_EMPTY = 3 * P_STAGES,
+              PB_TFULL = 4 * P_STAGES, PB_TEMPTY = 4 * P_STAGES + 2;
+constexpr int P_NBARS = 4 * P_STAGES + 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_cluster(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity);
+}
+// TMA load whose completion bytes are credited to a barrier of the LEADER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int ACT, bool PE, bool RESID>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
+                const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t stage0 = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(BAR(PB_AFULL + s), 1);       // local: this CTA's A tile
+      mbar_init(BAR(PB_WFULL + s), 1);       // leader: both W halves (one expect_tx arrive by the leader)
+      mbar_init(BAR(PB_CONV + s), 8);        // leader: one arrive per converter warp of both CTAs
+      mbar_init(BAR(PB_EMPTY + s), 1);       // local, multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(BAR(PB_TFULL + a), 1);                    // local, multicast tcgen05.commit
+      mbar_init(BAR(PB_TEMPTY + a), 2 * EPI_WARPS);       // leader: one arrive per epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // both CTAs' barriers are initialised before anyone signals across
+  tc_fence_after();
+  // the whole TMEM (512 columns) is allocated, so the base can only be 0: using the literal keeps every
+  // TMEM address warp-uniform for the compiler (see elect_one)
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
+
+  const int nkb = (int)((g.K + TBK - 1) / TBK);
+  const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;   // pair tiles (256 rows)
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    uint32_t stage = 0, phase = 0;
+    int tr_i = 0;
+    for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
+      const int nt = (int)(tile % g.n_tiles);
+      const int64_t mt = tile / g.n_tiles;
+      const int batch = (int)(mt / g.m_tiles_per_batch);
+      const int mi0 = (int)(mt % g.m_tiles_per_batch) * 2 * TBM + (int)rank * TBM;
+      int64_t nrem = g.N - (int64_t)nt * TBN;
+      const int n_mma = nrem >= TBN ? TBN : (int)((nrem + 15) & ~15LL);
+      const int wrow = nt * TBN + (int)rank * (n_mma / 2);       // this CTA's half of the W rows of the tile
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait_cluster(BAR(PB_EMPTY + stage), phase ^ 1);
+        if (lane == 0) trace_ev(g, 0, tr_i);
+        ++tr_i;
+        const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
+        const uint32_t wbar = mapa(BAR(PB_WFULL + stage), 0);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(PB_AFULL + stage), TILE_BYTES);
+          tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(PB_AFULL + stage));
+          if (leader) mbar_expect_tx(BAR(PB_WFULL + stage), 2 * TILE_BYTES);     // 4 x 8 KB from the two CTAs
+          tma_load_2d_pair(sb + TILE_BYTES, &tmWh, kb * TBK, wrow, wbar);
+          tma_load_2d_pair(sb + TILE_BYTES + TILE_BYTES / 2, &tmWl, kb * TBK, wrow, wbar);
+        }
+        __syncwarp();
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      uint32_t stage = 0, phase = 0;
+      int64_t it = 0;
+      int tr_i = 0;
+      for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const int nt = (int)(tile % g.n_tiles);
+        int64_t nrem = g.N - (int64_t)nt * TBN;
+        const uint32_t n_mma = nrem >= TBN ? (uint32_t)TBN : (uint32_t)((nrem + 15) & ~15LL);
+        // M = 256 across the pair
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((256u >> 4) << 24);
+        const uint32_t acc = (uint32_t)(it & 1);
+        mbar_wait_cluster(BAR(PB_TEMPTY + acc), (uint32_t)((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * TBN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_cluster(BAR(PB_WFULL + stage), phase);
+          mbar_wait_cluster(BAR(PB_CONV + stage), phase);
+          tc_fence_after();
+          if (lane == 0) trace_ev(g, 3, tr_i);
+          const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
+          const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + TILE_BYTES + TILE_BYTES / 2);
+          const uint32_t a_hi = tmem_base + TMEM_A0 + stage * 64, a_lo = a_hi + 32;
+          if (elect_one()) {
+#pragma unroll
+            for (int k4 = 0; k4 < TBK / 8; ++k4) {
+              const uint64_t adv = (uint64_t)(k4 * 2);
+              umma_tf32_ts_pair(tmem_d, a_lo + 8 * k4, db_hi + adv, idesc, (kb | k4) != 0);
+              umma_tf32_ts_pair(tmem_d, a_hi + 8 * k4, db_lo + adv, idesc, 1);
+              umma_tf32_ts_pair(tmem_d, a_hi + 8 * k4, db_hi + adv, idesc, 1);
+            }
+            umma_commit_pair(BAR(PB_EMPTY + stage));
+            if (kb == nkb - 1) umma_commit_pair(BAR(PB_TFULL + acc));
+            trace_ev(g, 4, tr_i);
+          }
+          ++tr_i;
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converters (both CTAs): own A rows -> (hi, lo) -> own TMEM =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
+    uint32_t stage = 0, phase = 0;
+    int tr_i = 0;
+    for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(BAR(PB_AFULL + stage), phase);
+        if (threadIdx.x == 64) trace_ev(g, 1, tr_i);
+        const uint8_t* arow = smem + stage * P_STAGE_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+          hi[4 * c + 0] = rna_tf32(v.x); lo[4 * c + 0] = rna_tf32(v.x - __uint_as_float(hi[4 * c + 0]));
+          hi[4 * c + 1] = rna_tf32(v.y); lo[4 * c + 1] = rna_tf32(v.y - __uint_as_float(hi[4 * c + 1]));
+          hi[4 * c + 2] = rna_tf32(v.z); lo[4 * c + 2] = rna_tf32(v.z - __uint_as_float(hi[4 * c + 2]));
+          hi[4 * c + 3] = rna_tf32(v.w); lo[4 * c + 3] = rna_tf32(v.w - __uint_as_float(hi[4 * c + 3]));
+        }
+        tc_fence_after();
+        tmem_st32(lane_addr + stage * 64, hi);
+        tmem_st32(lane_addr + stage * 64 + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa(BAR(PB_CONV + stage), 0));
+        if (threadIdx.x == 64) trace_ev(g, 2, tr_i);
+        ++tr_i;
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
+    const int q = warp & 3;
+    const int chalf = (warp - 6) >> 2;
+    uint8_t* stg = smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES;
+    const int cc = lane & 7, rsub = lane >> 3;
+    int64_t it = 0;
+    for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      const int nt = (int)(tile % g.n_tiles);
+      const int64_t mt = tile / g.n_tiles;
+      const int64_t batch = mt / g.m_tiles_per_batch;
+      const int64_t mi0 = (mt % g.m_tiles_per_batch) * 2 * TBM + (int64_t)rank * TBM + q * 32;
+      const int64_t ncol0 = (int64_t)nt * TBN;
+      const int64_t nrem = g.N - ncol0;
+      const int nchunks = nrem >= TBN ? 4 : (int)((nrem + 31) >> 5);
+      const uint32_t acc = (uint32_t)(it & 1);
+      const uint32_t tempty = mapa(BAR(PB_TEMPTY + acc), 0);
+      mbar_wait_cluster(BAR(PB_TFULL + acc), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
+      if (c_begin >= c_end) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty);
+        continue;
+      }
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
+        if (c == c_end - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty);
+        }
+        {
+          uint8_t* srow = stg + lane * 128;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
+                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+        __syncwarp();
+        const int64_t n = ncol0 + c * 32 + 4 * cc;
+        const bool col_ok = n < g.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
+        if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
+        const bool act_on = ACT != ACT_NONE && n >= g.act_from;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rsub;
+          const int64_t mi = mi0 + rr;
+          float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          if (!col_ok || mi >= g.rows_per_batch) continue;
+          const int64_t m = batch * g.rows_per_batch + mi;
+          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (act_on) {
+            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
+            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+          }
+          if (PE) {
+            float4 p4 = pf4;
+            if (n < g.pe_half) p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + mi * g.pe_half + n));
+            x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
+          }
+          if (RESID) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(g.resid + m * g.ldr + n));
+            x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+          }
+          *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = x;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();           // nobody leaves while the peer may still signal or read it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
 // w (n) -> hl[0..n) = rna_tf32(w), hl[n..2n) = rna_tf32(w - hi)
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hl,
                                                          int64_t n) {
@@ -438,6 +796,8 @@ bool make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dim
 
 }  // namespace
 
+long long* g_trace = nullptr;   // set by vasr_debug_gemm_trace (tools/gemm_trace.py)
+
 bool gemm_tc_supported(const GemmArgs& g) {
   if (!encode_fn()) return false;
   if (g.K % 4 != 0 || g.lda % 4 != 0 || g.batch_stride % 4 != 0) return false;
@@ -468,6 +828,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   if (g.pe_time && g.pe_rows != rpb) return cudaErrorNotSupported;   // pos-enc row == row within the batch
   const int64_t bstride = g.rows_per_batch > 0 ? g.batch_stride : rpb * g.lda;
 
+  // the CTA-pair kernel is correct but currently slower than the single-CTA one (its converter -> leader
+  // signalling is a cluster-scope arrive per warp per k-step): opt-in with VASR_GEMM=tc2
+  static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return e && strcmp(e, "tc2") == 0; }();
+  const bool pair = use_pair && num_sms >= 2;
   CUtensorMap tmA, tmWh, tmWl;
   {
     const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)rpb, (uint64_t)nb};
@@ -478,7 +842,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.K * 4};
-    const uint32_t box[2] = {TBK, TBN};
+    const uint32_t box[2] = {TBK, (uint32_t)(pair ? TBN / 2 : TBN)};     // a CTA of a pair loads half of the W tile
     if (!make_map(&tmWh, g.W_split, 2, dims, str, box)) return cudaErrorNotSupported;
     if (!make_map(&tmWl, g.W_split + g.N * g.K, 2, dims, str, box)) return cudaErrorNotSupported;
   }
@@ -486,26 +850,39 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.M = g.M; a.N = g.N; a.K = g.K;
   a.rows_per_batch = rpb;
   a.n_batches = nb;
-  a.m_tiles_per_batch = (int)((rpb + TBM - 1) / TBM);
+  a.m_tiles_per_batch = (int)((rpb + (pair ? 2 : 1) * TBM - 1) / ((pair ? 2 : 1) * TBM));
   a.n_tiles = (int)((g.N + TBN - 1) / TBN);
   a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act_from = g.act_from;
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
+  a.trace = g_trace;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
-  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+  const int64_t units = pair ? num_sms / 2 : num_sms;
+  const unsigned grid = (unsigned)((tiles < units ? tiles : units) * (pair ? 2 : 1));
   const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;
   cudaError_t err = cudaSuccess;
-  auto go = [&](auto kernel) {
+  auto go1 = [&](auto kernel) {
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (err == cudaSuccess) kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
   };
-#define VASR_TC_CASE(ACTV)                                                  \
-  if (g.act == ACTV) {                                                      \
-    if (pe && rs) go(gemm_tc_kernel<ACTV, true, true>);                     \
-    else if (pe) go(gemm_tc_kernel<ACTV, true, false>);                     \
-    else if (rs) go(gemm_tc_kernel<ACTV, false, true>);                     \
-    else go(gemm_tc_kernel<ACTV, false, false>);                            \
+  auto go2 = [&](auto kernel) {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
+  };
+#define VASR_TC_CASE(ACTV)                                                                   \
+  if (g.act == ACTV) {                                                                       \
+    if (pair) {                                                                              \
+      if (pe && rs) go2(gemm_tc2_kernel<ACTV, true, true>);                                  \
+      else if (pe) go2(gemm_tc2_kernel<ACTV, true, false>);                                  \
+      else if (rs) go2(gemm_tc2_kernel<ACTV, false, true>);                                  \
+      else go2(gemm_tc2_kernel<ACTV, false, false>);                                         \
+    } else {                                                                                 \
+      if (pe && rs) go1(gemm_tc_kernel<ACTV, true, true>);                                   \
+      else if (pe) go1(gemm_tc_kernel<ACTV, true, false>);                                   \
+      else if (rs) go1(gemm_tc_kernel<ACTV, false, true>);                                   \
+      else go1(gemm_tc_kernel<ACTV, false, false>);                                          \
+    }                                                                                        \
   }
   VASR_TC_CASE(ACT_NONE)
   VASR_TC_CASE(ACT_GELU)

@@ -39,6 +39,7 @@ cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches);
 cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64_t* launches);
 // hl[0..n) = rna_tf32(w), hl[n..2n) = rna_tf32(w - hl[0..n)): the weight operand of launch_gemm_tc.
 cudaError_t launch_split_tf32(const float* w, float* hl, int64_t n, cudaStream_t s);
+extern long long* g_trace;   // debug: device buffer (5 x 128 clock64 slots) CTA 0 of the projection kernel writes
 
 // ---------------------------------------------------------------- normalisation / conv ---
 // y[m, :] = LayerNorm(x[m, :]) * gamma + beta over C channels (eps 1e-5, biased variance).
