@@ -10,7 +10,7 @@ lib = _native.lib()
 lib._FuncPtr  # noqa
 fn = lib.vasr_debug_gemm_trace
 fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p]
-M, K, N = 48064, 192, 768
+M, K, N = [int(v) for v in sys.argv[1:4]] if len(sys.argv) > 3 else (48064, 192, 768)
 x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
 ws = va.split_tf32(w)
 for _ in range(3): va.linear(x, w, None, tensor_cores=True, weight_split=ws)
@@ -22,7 +22,10 @@ fn(None)
 t = buf.cpu().view(5, 128)
 base = int(t[0, 0])
 print("stage   P(issue)  C0(full)  C1(conv)  M0(go)  M1(issued) | tma=C0-P conv=C1-C0 wake=M0-C1 issue=M1-M0 period=P[i]-P[i-1]")
-for i in range(40):
+import statistics
+per = [int(t[0, i]) - int(t[0, i - 1]) for i in range(8, 100)]
+print('median period', statistics.median(per), 'mean', sum(per) / len(per), 'kernel span (CTA 0, first 128 stages)', int(t[4, 127]) - base)
+for i in range(int(os.environ.get('ROWS', '40'))):
     P, C0, C1, M0, M1 = [int(t[r, i]) - base for r in range(5)]
     prev = int(t[0, i - 1]) - base if i else 0
     print(f"{i:3d} {P:9d} {C0:9d} {C1:9d} {M0:8d} {M1:9d} | {C0-P:6d} {C1-C0:6d} {M0-C1:6d} {M1-M0:6d} {P-prev:6d}")

@@ -195,8 +195,18 @@ struct TcArgs {
   const float* pe_time;
   const float* pe_freq;
   int pe_half;
+  int rotate_n;       // rotate the n-tile index by the round number (see tile_coords)
   long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
 };
+// tile -> (m tile, n tile).  A persistent CTA takes tiles blockIdx.x, + gridDim.x, ...; with an n-tile
+// count that divides the grid every tile of a CTA would have the same n index, and the CTAs that own
+// the narrow last n-tile would do half the work of the others.  The n index is therefore rotated by
+// the round number, so each CTA sees every n-tile in turn.
+__device__ __forceinline__ void tile_coords(const TcArgs& g, int64_t tile, int64_t units, int64_t* mt, int* nt) {
+  *mt = tile / g.n_tiles;
+  const int64_t per = units / g.n_tiles > 0 ? units / g.n_tiles : 1;
+  *nt = (int)((tile % g.n_tiles + (g.rotate_n ? *mt / per : 0)) % g.n_tiles);
+}
 constexpr int TRACE_SLOTS = 128;
 __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
@@ -244,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
+  const int64_t UNITS = gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -251,8 +262,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0;
     int tr_i = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % g.n_tiles);
-      const int64_t mt = tile / g.n_tiles;
+      int nt;
+      int64_t mt;
+      tile_coords(g, tile, UNITS, &mt, &nt);
       const int batch = (int)(mt / g.m_tiles_per_batch);
       const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -276,7 +288,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int64_t it = 0;
     int tr_i = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = (int)(tile % g.n_tiles);
+      int nt;
+      int64_t mt_unused;
+      tile_coords(g, tile, UNITS, &mt_unused, &nt);
       // columns of this tile that exist, rounded up to the MMA's N granularity (16)
       int64_t nrem = g.N - (int64_t)nt * TBN;
       const uint32_t n_mma = nrem >= TBN ? (uint32_t)TBN : (uint32_t)((nrem + 15) & ~15LL);
@@ -359,8 +373,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cc = lane & 7, rsub = lane >> 3;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = (int)(tile % g.n_tiles);
-      const int64_t mt = tile / g.n_tiles;
+      int nt;
+      int64_t mt;
+      tile_coords(g, tile, UNITS, &mt, &nt);
       const int64_t batch = mt / g.m_tiles_per_batch;
       const int64_t mi0 = (mt % g.m_tiles_per_batch) * TBM + q * 32;    // first row (within the batch) of this warp
       const int64_t ncol0 = (int64_t)nt * TBN;
@@ -560,14 +575,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;   // pair tiles (256 rows)
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int64_t UNITS = npairs;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     uint32_t stage = 0, phase = 0;
     int tr_i = 0;
     for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
-      const int nt = (int)(tile % g.n_tiles);
-      const int64_t mt = tile / g.n_tiles;
+      int nt;
+      int64_t mt;
+      tile_coords(g, tile, UNITS, &mt, &nt);
       const int batch = (int)(mt / g.m_tiles_per_batch);
       const int mi0 = (int)(mt % g.m_tiles_per_batch) * 2 * TBM + (int)rank * TBM;
       int64_t nrem = g.N - (int64_t)nt * TBN;
@@ -597,7 +614,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int64_t it = 0;
       int tr_i = 0;
       for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
-        const int nt = (int)(tile % g.n_tiles);
+        int nt;
+        int64_t mt_unused;
+        tile_coords(g, tile, UNITS, &mt_unused, &nt);
         int64_t nrem = g.N - (int64_t)nt * TBN;
         const uint32_t n_mma = nrem >= TBN ? (uint32_t)TBN : (uint32_t)((nrem + 15) & ~15LL);
         // M = 256 across the pair
@@ -673,8 +692,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cc = lane & 7, rsub = lane >> 3;
     int64_t it = 0;
     for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
-      const int nt = (int)(tile % g.n_tiles);
-      const int64_t mt = tile / g.n_tiles;
+      int nt;
+      int64_t mt;
+      tile_coords(g, tile, UNITS, &mt, &nt);
       const int64_t batch = mt / g.m_tiles_per_batch;
       const int64_t mi0 = (mt % g.m_tiles_per_batch) * 2 * TBM + (int64_t)rank * TBM + q * 32;
       const int64_t ncol0 = (int64_t)nt * TBN;
@@ -856,6 +876,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
   a.trace = g_trace;
+  static const int rot_env = [] { const char* e = getenv("VASR_TC_ROT"); return e ? atoi(e) : 1; }();
+  a.rotate_n = rot_env;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
   const int64_t units = pair ? num_sms / 2 : num_sms;
