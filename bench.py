@@ -349,7 +349,10 @@ def run_own_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "scan_seq_kernel<LPR=4, 4 warps, 2 rows/lane, structured A> (8 local SSM layers)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the
+                         # ncu --set full capture summarised in profiles/r01_ncu_full_summary.md
+                         "traffic": 301809920 if (B, L, di, cfg.ssm_state_dim) == (64, 751, 384, 64) else None,
                          "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": local_ms,
                          "scan_launches_per_step": n_scan, "scan_ms_per_step": scan_total_ms,
                          "scan_share_of_step": scan_total_ms / step_total_ms,

@@ -1,4 +1,3 @@
 #!/bin/bash
 # scan kernel variants at config-2 shape; run on the GPU box
-for w in 3 4; do echo "WARPS=$w"; VASR_SCAN_WARPS=$w python tools/scan_bench.py --quick; done
-echo "RPL=1"; VASR_SCAN_RPL=1 python tools/scan_bench.py --quick
+for r in 2 3; do echo "RPL=$r"; VASR_SCAN_RPL=$r python tools/scan_bench.py --quick; done

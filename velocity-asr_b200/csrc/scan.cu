@@ -298,8 +298,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1 or 2)
-__global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
+template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1, 2 or 3)
+__global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
   constexpr int N = LPR * 16;
   constexpr int GROUPS = 32 / LPR;             // lane groups per warp
   constexpr int ROWS = WARPS * GROUPS * RPL;   // rows per CTA
@@ -420,6 +420,35 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
     return hsum2(add2(acc0, acc1));
   };
 
+  // Structured A: the per-row set-up (u, the three ex2 and the first power quad) of step t+1 is computed
+  // DURING step t, split in two phases placed between the row updates, so that neither the LDS nor the
+  // MUFU latency is ever waited for (warps issue in order: ncu showed the first multiply after the ex2
+  // as the top stall of the previous version).
+  struct Pre {
+    u64 uu[RPL], Pa[RPL], Pb[RPL], rq2[RPL];
+  };
+  auto row_step_pre = [&](u64 (&Hr)[8], u64 uu, u64 Pa, u64 Pb, u64 rq2, const ulonglong2 (&bq)[4],
+                          const ulonglong2 (&cq)[4]) {
+    u64 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      Hr[2 * m] = fma2(Pa, Hr[2 * m], mul2(uu, bq[m].x));
+      Hr[2 * m + 1] = fma2(Pb, Hr[2 * m + 1], mul2(uu, bq[m].y));
+      if (m == 0) {
+        acc0 = mul2(Hr[0], cq[0].x);
+        acc1 = mul2(Hr[1], cq[0].y);
+      } else {
+        acc0 = fma2(Hr[2 * m], cq[m].x, acc0);
+        acc1 = fma2(Hr[2 * m + 1], cq[m].y, acc1);
+      }
+      if (m < 3) {
+        Pa = mul2(Pa, rq2);
+        Pb = mul2(Pb, rq2);
+      }
+    }
+    return hsum2(add2(acc0, acc1));
+  };
+
   // operands of one timestep, fetched one step ahead of their use
   struct Ops {
     ulonglong2 bq[4], cq[4];
@@ -436,7 +465,8 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
       const float2 x2 = *reinterpret_cast<const float2*>(pX + t * ROWS);
       o.dt[0] = d2.x; o.dt[RPL - 1] = d2.y; o.x[0] = x2.x; o.x[RPL - 1] = x2.y;
     } else {
-      o.dt[0] = pD[t * ROWS]; o.x[0] = pX[t * ROWS];
+#pragma unroll
+      for (int r = 0; r < RPL; ++r) { o.dt[r] = pD[t * ROWS + r]; o.x[r] = pX[t * ROWS + r]; }
     }
   };
 
@@ -479,8 +509,12 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
         }
       }
       if (sp < fvalid) {
-        if (RPL == 2) *reinterpret_cast<float2*>(fy + sp * a.ldy) = make_float2(y[0], y[RPL - 1]);
-        else fy[sp * a.ldy] = y[0];
+        if (RPL == 2) {
+          *reinterpret_cast<float2*>(fy + sp * a.ldy) = make_float2(y[0], y[RPL - 1]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < RPL; ++r) fy[sp * a.ldy + r] = y[r];
+        }
       }
     }
   };
@@ -503,6 +537,31 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
 
     Ops cur;
     load_ops(cur, pB, pC, pX, pD, 0);
+    Pre pre;
+    auto mufu_phase = [&](const Ops& o, float (&r)[RPL], float (&e)[RPL], float (&rq)[RPL]) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        r[q] = ex2_approx(o.dt[q] * c_r);
+        e[q] = ex2_approx(o.dt[q] * c_e);
+        rq[q] = ex2_approx(o.dt[q] * c_q);
+      }
+    };
+    auto pack_phase = [&](const Ops& o, const float (&r)[RPL], const float (&e)[RPL], const float (&rq)[RPL], Pre& p) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const float u = o.x[q] * o.dt[q];
+        const float r2 = r[q] * r[q];
+        p.uu[q] = pack2(u, u);
+        p.Pa[q] = pack2(e[q], e[q] * r[q]);
+        p.Pb[q] = mul2(p.Pa[q], pack2(r2, r2));
+        p.rq2[q] = pack2(rq[q], rq[q]);
+      }
+    };
+    if (STRUCT) {
+      float r[RPL], e[RPL], rq[RPL];
+      mufu_phase(cur, r, e, rq);
+      pack_phase(cur, r, e, rq, pre);
+    }
 #pragma unroll 1
     for (int g4 = 0; g4 < TCH; g4 += 4) {
       if (g4 >= tcn) break;
@@ -512,8 +571,20 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
         const int t = g4 + i;
         Ops nxt;
         load_ops(nxt, pB, pC, pX, pD, t + 1 < TCH ? t + 1 : TCH - 1);
+        if (STRUCT) {
+          float r[RPL], e[RPL], rq[RPL];
+          Pre npre;
+          yp[RPL * i] = row_step_pre(H[0], pre.uu[0], pre.Pa[0], pre.Pb[0], pre.rq2[0], cur.bq, cur.cq);
+          mufu_phase(nxt, r, e, rq);
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) yp[RPL * i + r] = row_step(H[r], cur.dt[r], cur.x[r], cur.bq, cur.cq);
+          for (int q = 1; q < RPL; ++q)
+            yp[RPL * i + q] = row_step_pre(H[q], pre.uu[q], pre.Pa[q], pre.Pb[q], pre.rq2[q], cur.bq, cur.cq);
+          pack_phase(nxt, r, e, rq, npre);
+          pre = npre;
+        } else {
+#pragma unroll
+          for (int r = 0; r < RPL; ++r) yp[RPL * i + r] = row_step(H[r], cur.dt[r], cur.x[r], cur.bq, cur.cq);
+        }
         cur = nxt;
       }
       // x and z of the values this lane will finalise one block from now
@@ -527,8 +598,11 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 2 ? 384 : 640) / (WARPS * 
           nfx[sp * RPL] = x2.x; nfx[sp * RPL + RPL - 1] = x2.y;
           nfz[sp * RPL] = z2.x; nfz[sp * RPL + RPL - 1] = z2.y;
         } else {
-          nfx[sp] = pX[(s0 + sp) * ROWS];
-          nfz[sp] = gate ? pZ[(s0 + sp) * ROWS] : 0.f;
+#pragma unroll
+          for (int r = 0; r < RPL; ++r) {
+            nfx[sp * RPL + r] = pX[(s0 + sp) * ROWS + r];
+            nfz[sp * RPL + r] = gate ? pZ[(s0 + sp) * ROWS + r] : 0.f;
+          }
         }
       }
       finalize();                          // the PREVIOUS block
@@ -559,7 +633,7 @@ cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// picks the CTA shape: rows per CTA must divide Di.  VASR_SCAN_RPL=1|2 overrides rows per lane.
+// picks the CTA shape: rows per CTA must divide Di.  VASR_SCAN_RPL=1|2|3 overrides rows per lane.
 template <int LPR>
 cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
   constexpr int G = 32 / LPR;
