@@ -126,6 +126,23 @@ int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S,
 int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64_t S,
                          int32_t* tokens_host, int32_t* lens_host);
 
+/* ---- config 5: FakeQuantize of the 12 non-SSM modules (velocity_asr/quantize.py)
+ * prepare_model_for_qat (quantize.py:269-322, ssm_state_fp32 = True) replaces temporal_binding.conv,
+ * pool1/pool2.pool_proj, cross_attention.{q,k,v,out}_proj, fusion.{gate_proj.0,local_proj,global_proj,
+ * out_proj} and ctc_head.proj.2 by QuantizedLinear / QuantizedConv1d: per-output-channel symmetric int8
+ * FakeQuantize of the weight, fp32 matmul, per-tensor asymmetric uint8 FakeQuantize of the output
+ * (quantize.py:180-191, 248-266).  vasr_set_quantization(h, 1) + vasr_commit_weights applies the weight side
+ * (the module's own weights are kept, unlike the reference, which re-initialises them: SURVEY.md 5.8);
+ * output nodes pass through until calibrated (quantize.py:82-84).
+ * vasr_calibrate runs one forward on mel (B, T, mel_bins) with the output nodes in training mode: each takes
+ * min / max of the tensor it is about to quantise, sets scale / zero point (quantize.py:99-121) and
+ * quantises with them; the values stay for later forwards (calibrate_model, quantize.py:325-371).
+ * module = reference module name, e.g. "ctc_head.proj.2". */
+int vasr_set_quantization(vasr_handle* h, int enabled);
+int vasr_calibrate(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, void* stream);
+int vasr_get_quant_params(vasr_handle* h, const char* module, float* scale, float* zero_point);
+int vasr_set_quant_params(vasr_handle* h, const char* module, float scale, float zero_point);
+
 /* ---- a plain linear layer (F.linear), exposed so the GEMM kernel can be tested alone.
  * act: 0 none, 1 gelu(erf), 2 softplus, 3 sigmoid.  x (M, K) stride ldx, w (N, K), bias (N) or
  * NULL, out (M, N) stride ldo.  K % 16 == 0. */

@@ -160,6 +160,55 @@ def linear(x, w, b=None):
     return y if b is None else y + b
 
 
+class QuantState:
+    """Config 5: which modules are QuantizedLinear / QuantizedConv1d (quantize.py:269-322 with
+    ssm_state_fp32: everything outside sub-trees whose name contains "ssm"), the output FakeQuantize
+    parameters gathered so far, and whether the nodes are in training mode (calibrating)."""
+    MODULES = (
+        "temporal_binding.conv",
+        "global_context.pool1.pool_proj", "global_context.pool2.pool_proj",
+        "global_context.cross_attention.q_proj", "global_context.cross_attention.k_proj",
+        "global_context.cross_attention.v_proj", "global_context.cross_attention.out_proj",
+        "global_context.fusion.gate_proj.0", "global_context.fusion.local_proj",
+        "global_context.fusion.global_proj", "global_context.fusion.out_proj",
+        "ctc_head.proj.2",
+    )
+
+    def __init__(self, act=None, calibrating: bool = False):
+        self.act = dict(act or {})          # module -> (scale, zero_point)
+        self.calibrating = calibrating
+
+
+def quantized_weight(w):
+    """QuantizedLinear / QuantizedConv1d weight path: per-output-channel symmetric int8 FakeQuantize,
+    forward value x + (dq - x).  quantize.py:99-133, 182-183"""
+    scale, zp = fake_quant_params(w, symmetric=True, per_channel=True)
+    return w + (fake_quantize(w, scale, zp, symmetric=True) - w)
+
+
+def quantized_output(out, name: str, q: "QuantState"):
+    """The activation_quantizer of a quantised module (asymmetric per-tensor uint8): in training mode it
+    first takes its scale / zero point from `out` (quantize.py:86-88); un-calibrated nodes pass through
+    (quantize.py:82-84)."""
+    if q.calibrating:
+        scale, zp = fake_quant_params(out, symmetric=False, per_channel=False)
+        q.act[name] = (float(scale), float(zp))
+    if name not in q.act:
+        return out
+    scale, zp = q.act[name]
+    return out + (fake_quantize(out, scale, zp, symmetric=False) - out)
+
+
+def qlinear(x, sd, name: str, q, dtype=np.float64):
+    """nn.Linear `name` of the state dict, or its QuantizedLinear replacement when q is given.
+    quantize.py:180-191"""
+    w = sd[name + ".weight"].astype(dtype)
+    b = sd[name + ".bias"].astype(dtype)
+    if q is None:
+        return linear(x, w, b)
+    return quantized_output(linear(x, quantized_weight(w), b), name, q)
+
+
 # --------------------------------------------------------------------------
 # a2  temporal binding  (model.py:94-127, 176-202)
 # --------------------------------------------------------------------------
@@ -176,12 +225,14 @@ def positional_time_table(n_rows: int, d_model: int = 192, dtype=np.float64) -> 
     return pe.astype(dtype)
 
 
-def temporal_binding(mel: np.ndarray, sd: Dict[str, np.ndarray], dtype=np.float64) -> np.ndarray:
+def temporal_binding(mel: np.ndarray, sd: Dict[str, np.ndarray], dtype=np.float64, q=None) -> np.ndarray:
     """Conv1d(mel_bins->d_model, k=3, stride=2, pad=1) -> GELU -> + [pe_time | pe_freq] -> LN.
 
     model.py:187-200.  (B,T,80) -> (B,(T+1)//2,192)."""
     p = "temporal_binding."
     w = sd[p + "conv.weight"].astype(dtype)          # (192, 80, 3)
+    if q is not None:
+        w = quantized_weight(w)                      # QuantizedConv1d, quantize.py:248-266
     b = sd[p + "conv.bias"].astype(dtype)
     mel = np.asarray(mel, dtype=dtype)
     B, T, C = mel.shape
@@ -191,7 +242,10 @@ def temporal_binding(mel: np.ndarray, sd: Dict[str, np.ndarray], dtype=np.float6
     out = np.zeros((B, L, w.shape[0]), dtype=dtype)
     for j in range(3):
         out += xp[:, j:j + 2 * L:2][:, :L] @ w[:, :, j].T
-    out = gelu(out + b)
+    out = out + b
+    if q is not None:
+        out = quantized_output(out, "temporal_binding.conv", q)
+    out = gelu(out)
     pe_time = sd[p + "pos_encoding.pe_time"].astype(dtype)
     if pe_time.shape[0] < L:
         raise RuntimeError(f"pe_time has {pe_time.shape[0]} rows < {L} tokens (model.py:125)")
@@ -382,12 +436,12 @@ def adaptive_avg_pool(x, K: int):
     return out
 
 
-def multi_head_attention(q_in, kv_in, sd, p, heads, dtype=np.float64):
+def multi_head_attention(q_in, kv_in, sd, p, heads, dtype=np.float64, qs=None):
     """MultiHeadAttention.forward (no mask, dropout = identity).  attention.py:135-162"""
     g = lambda k: sd[p + k].astype(dtype)
-    q = linear(q_in, g("q_proj.weight"), g("q_proj.bias"))
-    k = linear(kv_in, g("k_proj.weight"), g("k_proj.bias"))
-    v = linear(kv_in, g("v_proj.weight"), g("v_proj.bias"))
+    q = qlinear(q_in, sd, p + "q_proj", qs, dtype)
+    k = qlinear(kv_in, sd, p + "k_proj", qs, dtype)
+    v = qlinear(kv_in, sd, p + "v_proj", qs, dtype)
     Bsz, Lq, Adim = q.shape
     hd = Adim // heads
     q = q.reshape(Bsz, Lq, heads, hd).transpose(0, 2, 1, 3)
@@ -398,41 +452,42 @@ def multi_head_attention(q_in, kv_in, sd, p, heads, dtype=np.float64):
     a = np.exp(s)
     a = a / a.sum(axis=-1, keepdims=True)
     o = (a @ v).transpose(0, 2, 1, 3).reshape(Bsz, Lq, Adim)
-    return linear(o, g("out_proj.weight"), g("out_proj.bias"))
+    return qlinear(o, sd, p + "out_proj", qs, dtype)
 
 
-def gated_fusion(loc, ctx, sd, p, dtype=np.float64):
+def gated_fusion(loc, ctx, sd, p, dtype=np.float64, q=None):
     """g = sigmoid(W_g [loc|ctx]); out = W_o (g * W_l loc + (1-g) * W_c ctx).  attention.py:207-218"""
     g_ = lambda k: sd[p + k].astype(dtype)
-    gate = sigmoid(linear(np.concatenate([loc, ctx], axis=-1), g_("gate_proj.0.weight"), g_("gate_proj.0.bias")))
-    lt = linear(loc, g_("local_proj.weight"), g_("local_proj.bias"))
-    gt = linear(ctx, g_("global_proj.weight"), g_("global_proj.bias"))
-    return linear(gate * lt + (1.0 - gate) * gt, g_("out_proj.weight"), g_("out_proj.bias"))
+    p_ = p.rstrip(".")
+    gate = sigmoid(qlinear(np.concatenate([loc, ctx], axis=-1), sd, p_ + ".gate_proj.0", q, dtype))
+    lt = qlinear(loc, sd, p_ + ".local_proj", q, dtype)
+    gt = qlinear(ctx, sd, p_ + ".global_proj", q, dtype)
+    return qlinear(gate * lt + (1.0 - gate) * gt, sd, p_ + ".out_proj", q, dtype)
 
 
-def global_context(local, sd, cfg, dtype=np.float64):
+def global_context(local, sd, cfg, dtype=np.float64, q=None):
     """HierarchicalGlobalContext.forward.  attention.py:296-319.  GlobalSSM blocks are built
     without a scan_mode argument (ssm.py:529-538) so they always run the 'parallel' scan."""
     p = "global_context."
     g = lambda k: sd[p + k].astype(dtype)
     L = local.shape[1]
     k1, k2 = pool_sizes(L)
-    x1 = linear(adaptive_avg_pool(local, k1), g("pool1.pool_proj.weight"), g("pool1.pool_proj.bias"))
+    x1 = qlinear(adaptive_avg_pool(local, k1), sd, p + "pool1.pool_proj", q, dtype)
     xs = ssm_stack(x1, sd, p + "global_ssm.", cfg["global_ssm_layers"], "parallel", dtype)
-    x2 = linear(adaptive_avg_pool(xs, k2), g("pool2.pool_proj.weight"), g("pool2.pool_proj.bias"))
+    x2 = qlinear(adaptive_avg_pool(xs, k2), sd, p + "pool2.pool_proj", q, dtype)
     kv = layer_norm(x2, g("norm1.weight"), g("norm1.bias"))
-    q = layer_norm(local, g("norm2.weight"), g("norm2.bias"))
-    ctx = multi_head_attention(q, kv, sd, p + "cross_attention.", cfg["attention_heads"], dtype)
-    return gated_fusion(local, ctx, sd, p + "fusion.", dtype)
+    qn = layer_norm(local, g("norm2.weight"), g("norm2.bias"))
+    ctx = multi_head_attention(qn, kv, sd, p + "cross_attention.", cfg["attention_heads"], dtype, qs=q)
+    return gated_fusion(local, ctx, sd, p + "fusion.", dtype, q=q)
 
 
 # --------------------------------------------------------------------------
 # a11-a13  CTC head, whole forward, greedy decode
 # --------------------------------------------------------------------------
-def ctc_head(x, sd, dtype=np.float64):
+def ctc_head(x, sd, dtype=np.float64, q=None):
     """LayerNorm -> Linear(d_model -> vocab).  model.py:223-227"""
     g = lambda k: sd["ctc_head.proj." + k].astype(dtype)
-    return linear(layer_norm(x, g("0.weight"), g("0.bias")), g("2.weight"), g("2.bias"))
+    return qlinear(layer_norm(x, g("0.weight"), g("0.bias")), sd, "ctc_head.proj.2", q, dtype)
 
 
 DEFAULT_CFG = dict(mel_bins=80, d_model=192, ssm_layers=8, ssm_state_dim=64, ssm_expand_ratio=2,
@@ -440,13 +495,14 @@ DEFAULT_CFG = dict(mel_bins=80, d_model=192, ssm_layers=8, ssm_state_dim=64, ssm
                    attention_heads=4, attention_dim=48, vocab_size=1000, scan_mode="parallel")
 
 
-def forward(mel, sd, cfg=None, dtype=np.float64, return_features: bool = False):
-    """VELOCITYASR.forward.  model.py:350-368"""
+def forward(mel, sd, cfg=None, dtype=np.float64, return_features: bool = False, quant=None):
+    """VELOCITYASR.forward.  model.py:350-368.  quant: a QuantState -> the model after
+    prepare_model_for_qat with its weights kept (config 5)."""
     cfg = dict(DEFAULT_CFG, **(cfg or {}))
-    x = temporal_binding(mel, sd, dtype)
+    x = temporal_binding(mel, sd, dtype, q=quant)
     local = ssm_stack(x, sd, "local_ssm.", cfg["ssm_layers"], cfg["scan_mode"], dtype)
-    fused = global_context(local, sd, cfg, dtype)
-    logits = ctc_head(fused, sd, dtype)
+    fused = global_context(local, sd, cfg, dtype, q=quant)
+    logits = ctc_head(fused, sd, dtype, q=quant)
     if return_features:
         return logits, {"temporal_binding": x, "local_features": local, "fused_features": fused}
     return logits

@@ -303,6 +303,65 @@ def test_long_form_needs_longer_table(va):
     assert rel(f["temporal_binding"], ref_tb) < 1e-4
 
 
+# ------------------------------------------------------------------ config 5: FakeQuantize ---
+def test_quantized_model_matches_reference_golden(va, golden):
+    """prepare_model_for_qat + calibrate_model on the CUDA path against the reference run recorded in
+    tests/golden/quant.npz (recipe in tests/golden/make_golden_quant.py) and against the oracle."""
+    from velocity_asr.quantize import QUANTIZED_MODULES, read_quant_params
+    g = golden("quant")
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(QUANTIZED_MODULES)
+    m = make_model(va, "sequential")
+    mel_cal = va.compute_mel_spectrogram(FU.synth_audio(2, 16000).cuda())
+    mel_test = va.compute_mel_spectrogram(FU.synth_audio(2, 16000, seed=77).cuda())
+    fp32 = m(mel_test)
+    assert rel(fp32, g["logits_fp32"]) < 1e-3
+    va.prepare_model_for_qat(m)
+    # un-calibrated output nodes pass through (quantize.py:82-84): only the weights are on the int8 grid
+    sd = np_sd(m)
+    ref_w_only = O.forward(mel_test.double().cpu().numpy(), sd, dict(scan_mode="sequential"), quant=O.QuantState())
+    assert rel(m(mel_test), ref_w_only) < 1e-3
+    va.calibrate_model(m, [mel_cal])
+    got = read_quant_params(m)
+    for n, s_ref, z_ref in zip(names, g["act_scale"], g["act_zp"]):
+        s_, z_ = got[n]
+        assert abs(s_ - s_ref) < 1e-2 * s_ref and abs(z_ - z_ref) < 1.0, (n, s_, s_ref, z_, z_ref)
+    step = float(g["act_scale"][names.index("ctc_head.proj.2")])
+    # same grids as the reference: load its calibrated parameters, then compare logits
+    eng = m._engine(m._device())
+    for n, s_ref, z_ref in zip(names, g["act_scale"], g["act_zp"]):
+        va._native.check(eng.lib.vasr_set_quant_params(eng.handle, n.encode(), float(s_ref), float(z_ref)))
+    lq = m(mel_test).cpu().numpy()
+    d = np.abs(lq - g["logits_q"])
+    assert (d < 1e-3).mean() > 0.8, (d < 1e-3).mean()
+    assert d.max() <= 2.5 * step, (d.max(), step)
+    assert (lq.argmax(-1) == g["logits_q"].argmax(-1)).mean() >= 0.95
+    # every logit sits on the last quantiser's grid: (x / scale + zp) is an integer in [0, 255]
+    s_c, z_c = float(g["act_scale"][names.index("ctc_head.proj.2")]), float(g["act_zp"][names.index("ctc_head.proj.2")])
+    qv = lq.astype(np.float64) / s_c + z_c
+    assert np.abs(qv - np.rint(qv)).max() < 1e-2 and qv.min() > -0.5 and qv.max() < 255.5
+    # tokens: fused path == separate calls, and agree with the reference's argmax stream
+    audio = FU.synth_audio(2, 16000, seed=77)
+    assert m.transcribe(audio.cuda()) == va.ctc_greedy_decode(m(mel_test))
+
+
+def test_quantization_is_reversible_and_guarded(va):
+    m = make_model(va, "sequential")
+    mel = va.compute_mel_spectrogram(FU.synth_audio(1, 8000).cuda())
+    base = m(mel)
+    with pytest.raises(RuntimeError):
+        va.calibrate_model(m, [mel])                 # prepare_model_for_qat first
+    with pytest.raises(NotImplementedError):
+        va.prepare_model_for_qat(m, va.QuantizationConfig(weight_bits=4))
+    va.prepare_model_for_qat(m)
+    va.calibrate_model(m, [mel])
+    q = m(mel)
+    assert (q - base).abs().max() > 1e-3
+    assert torch.equal(m(mel), q)                    # deterministic
+    m._quantized = False
+    assert torch.equal(m(mel), base)                 # fp32 weights come back bit-identical
+
+
 # ------------------------------------------------------------------ CTC greedy -----------
 def test_ctc_greedy_known_answers(va, golden):
     g = golden("decode")

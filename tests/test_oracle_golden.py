@@ -130,3 +130,44 @@ def test_fake_quantize_arithmetic():
     np.testing.assert_allclose(s2, 3.0 / 255)
     assert np.abs(O.fake_quantize(x, s2, zp2, symmetric=False) - x).max() <= s2 / 2 + 1e-12
     assert O.fake_quantize(np.array([0.5, 1.5, 2.5]), 1.0, 0.0, True).tolist() == [0.0, 2.0, 2.0]  # half-to-even
+
+
+def test_quantized_forward_matches_reference(golden):
+    """Config 5: the oracle's quantised forward (weights kept, output nodes calibrated by one forward in
+    training mode) against the reference run by tests/golden/make_golden_quant.py.  Quantisation puts
+    values on a grid, so a fp64-vs-fp32 rounding difference right at a grid boundary moves an element by
+    one step: scales must agree tightly, logits almost everywhere, and never by more than a few steps."""
+    import torch
+    import velocity_asr as va
+    g = golden("quant")
+    torch.manual_seed(FU.WEIGHT_SEED)
+    sd_t = va.VELOCITYASR(va.VelocityASRConfig(scan_mode="sequential")).state_dict()
+    assert np.allclose(FU.state_dict_digest(sd_t), g["weights_digest"], rtol=0, atol=0)
+    sd = {k: v.numpy() for k, v in sd_t.items()}
+    mel_cal = O.log_mel(FU.synth_audio(2, 16000).numpy())
+    mel_test = O.log_mel(FU.synth_audio(2, 16000, seed=77).numpy())
+    cfg = dict(scan_mode="sequential")
+    q = O.QuantState(calibrating=True)
+    lc = O.forward(mel_cal, sd, cfg, quant=q)
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(O.QuantState.MODULES) == sorted(q.act)
+    for n, s_ref, z_ref in zip(names, g["act_scale"], g["act_zp"]):
+        s, z = q.act[n]
+        # extremes downstream of a quantised tensor move with single grid-boundary flips upstream
+        assert abs(s - s_ref) < 1e-2 * s_ref and abs(z - z_ref) < 1.0, (n, s, s_ref, z, z_ref)
+    step = float(g["act_scale"][names.index("ctc_head.proj.2")])
+    # own calibration: the output grid is shifted by the (tiny) differences in scale / zero point
+    assert np.abs(lc - g["logits_cal"]).max() <= 4.0 * step and np.abs(lc - g["logits_cal"]).mean() < step
+    # the reference's calibrated parameters: same grids, so equal up to boundary flips
+    q = O.QuantState(act={n: (float(s_), float(z_)) for n, s_, z_ in zip(names, g["act_scale"], g["act_zp"])})
+    lq = O.forward(mel_test, sd, cfg, quant=q)
+    d = np.abs(lq - g["logits_q"])
+    # eleven quantisers sit upstream of the logits: a value within rounding noise of a grid boundary flips
+    # by one step and drags some downstream values across theirs.  Most logits are identical, the rest are
+    # one (rarely two) steps of the last quantiser away, and the frame argmax is stable.
+    assert (d < 1e-3).mean() > 0.8, (d < 1e-3).mean()
+    assert d.max() <= 2.5 * step, (d.max(), step)
+    assert (lq.argmax(-1) == g["logits_q"].argmax(-1)).mean() >= 0.95
+    assert np.abs(g["logits_q"] - g["logits_fp32"]).max() > 5 * step       # quantisation is visible
+    wq = O.quantized_weight(sd["ctc_head.proj.2.weight"].astype(np.float64))[:8]
+    assert np.abs(wq - g["wq_ctc_rows"]).max() < 1e-7

@@ -65,6 +65,18 @@ __device__ __forceinline__ float softplus_t20(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// FakeQuantize of an output activation (quantize.py:86-133, asymmetric per-tensor uint8):
+//   q = clamp(round_half_even(x / scale + zp), 0, 255);  dq = (q - zp) * scale;  result x + (dq - x)
+// with the reference's own operation order (IEEE division, separately rounded add), so values land on the
+// same grid point unless x itself sits within rounding noise of a boundary.  scale <= 0 -> pass-through.
+__device__ __forceinline__ float fake_quant_u8(float x, float scale, float zp) {
+  if (!(scale > 0.f)) return x;
+  float q = rintf(__fadd_rn(__fdiv_rn(x, scale), zp));
+  q = fminf(fmaxf(q, 0.f), 255.f);
+  const float dq = __fmul_rn(__fsub_rn(q, zp), scale);
+  return __fadd_rn(x, __fsub_rn(dq, x));
+}
+
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SOFTPLUS = 2, ACT_SIGMOID = 3 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

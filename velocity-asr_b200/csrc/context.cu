@@ -87,7 +87,63 @@ __global__ void __launch_bounds__(256) gate_mix_kernel(const float* __restrict__
   out[idx] = g * r[C + c] + (1.0f - g) * r[2 * C + c];
 }
 
+// calibration of an output FakeQuantize node: one CTA, fixed reduction order -> run-to-run identical
+__global__ void __launch_bounds__(1024) minmax_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int c0,
+                                                      int nc, float* __restrict__ mm) {
+  __shared__ float smin[32], smax[32];
+  float lo = INFINITY, hi = -INFINITY;
+  const int64_t total = M * nc;
+  for (int64_t i = threadIdx.x; i < total; i += 1024) {
+    const float v = x[(i / nc) * ldx + c0 + (int)(i % nc)];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = smin[threadIdx.x];
+    hi = smax[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (threadIdx.x == 0) { mm[0] = lo; mm[1] = hi; }
+  }
+}
+
+__global__ void set_qparams_kernel(const float* __restrict__ mm, float* __restrict__ qs, float* __restrict__ qz,
+                                   int c0, int nc) {
+  // scale = (max - min) / (qmax - qmin), clamped to >= 1e-10; zp = qmin - min / scale  (quantize.py:116-121)
+  const float scale = fmaxf(__fdiv_rn(__fsub_rn(mm[1], mm[0]), 255.f), 1e-10f);
+  const float zp = __fsub_rn(0.f, __fdiv_rn(mm[0], scale));
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    qs[c0 + c] = scale;
+    qz[c0 + c] = zp;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_minmax(const float* x, int64_t ldx, int64_t M, int c0, int nc, float* mm, cudaStream_t s,
+                          int64_t* launches) {
+  if (M <= 0 || nc <= 0) return cudaErrorInvalidValue;
+  minmax_kernel<<<1, 1024, 0, s>>>(x, ldx, M, c0, nc, mm);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_qparams(const float* mm, float* q_scale, float* q_zp, int c0, int nc, cudaStream_t s,
+                               int64_t* launches) {
+  set_qparams_kernel<<<1, 128, 0, s>>>(mm, q_scale, q_zp, c0, nc);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_adaptive_pool(const float* x, int64_t ldx, float* out, int64_t B, int64_t L, int64_t K,
                                  int C, cudaStream_t s, int64_t* launches) {

@@ -49,6 +49,17 @@ struct BlockW {
   int structured = 0;
 };
 
+// One projection that hosts FakeQuantize'd reference modules (config 5): per-column output scale / zero
+// point on the device, and which column ranges belong to which module (quantize.py:142-191, 194-266).
+struct QSite {
+  float *qs = nullptr, *qz = nullptr;   // (N) device; scale <= 0 -> column not quantised / not calibrated
+  int N = 0;
+  int nmod = 0;
+  const char* name[3] = {nullptr, nullptr, nullptr};
+  int c0[3] = {0, 0, 0}, nc[3] = {0, 0, 0};
+};
+enum { Q_TB = 0, Q_P1, Q_P2, Q_Q, Q_KV, Q_O, Q_F3, Q_FO, Q_CTC, Q_SITES };
+
 struct Arena {
   char* base = nullptr;
   size_t bytes = 0;
@@ -72,6 +83,12 @@ struct vasr_handle {
   std::vector<void*> weight_allocs;
   std::vector<void*> frontend_allocs;
   std::vector<void*>* alloc_list = &weight_allocs;
+  // config 5: FakeQuantize of the 12 non-SSM modules (quantize.py:269-322 with ssm_state_fp32)
+  int quant = 0;             // requested; applied at commit
+  int quant_active = 0;      // the committed weights are fake-quantised and the sites below exist
+  int calibrating = 0;       // this forward updates the activation scales before using them
+  QSite qsite[Q_SITES];
+  float* q_mm = nullptr;     // (2) min / max scratch
   // TF32 hi/lo split of each weight matrix the tensor-core kernel has used, keyed by the fp32 copy
   std::unordered_map<const float*, float*> w_split;
 
@@ -143,6 +160,7 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
 struct Work {
   float *xp, *spec, *raw, *mean, *rstd, *melpad;
   double* part;
+  float* qscratch;      // probe output of a quantised projection during calibration (M x max N)
   float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
   float *ga, *gb, *g2, *g2n, *kv;
   float* logits;
@@ -188,6 +206,7 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   t.g2n = a.take<float>(q.M2 * q.d);
   t.kv = a.take<float>(q.M2 * 2 * q.att);
   if (need_logits) t.logits = a.take<float>(q.M * q.V);
+  if (h->quant_active) t.qscratch = a.take<float>(q.M * (q.V > 3 * q.d ? q.V : 3 * q.d));
   t.pred = a.take<int32_t>(q.M);
   if (need_stage) {
     t.pcm_stage = a.take<float>(q.B * q.S);
@@ -245,6 +264,42 @@ int up(vasr_handle* h, const std::string& k, int64_t numel, float** dst) {
   const std::vector<float>* v;
   RET(need(h, k, numel, &v));
   return upload(h, v->data(), v->size(), dst);
+}
+
+// FakeQuantize of a weight tensor, per output channel, symmetric int8, in the reference's operation order
+// (quantize.py:99-133 with symmetric=True, per_channel=True, channel_dim=0; forward returns x + (dq - x)).
+void fake_quant_rows(std::vector<float>& w, int64_t rows) {
+  const int64_t cols = rows > 0 ? (int64_t)w.size() / rows : 0;
+  for (int64_t r = 0; r < rows; ++r) {
+    float* x = w.data() + r * cols;
+    float lo = x[0], hi = x[0];
+    for (int64_t c = 1; c < cols; ++c) { lo = fminf(lo, x[c]); hi = fmaxf(hi, x[c]); }
+    float scale = fmaxf(fabsf(lo), fabsf(hi)) / 127.0f;
+    if (scale < 1e-10f) scale = 1e-10f;
+    for (int64_t c = 0; c < cols; ++c) {
+      volatile float t = x[c] / scale;          // separately rounded, as eager PyTorch does
+      float q = nearbyintf(t + 0.0f);
+      q = fminf(fmaxf(q, -128.f), 127.f);
+      volatile float dq = (q - 0.0f) * scale;
+      volatile float diff = dq - x[c];
+      x[c] = x[c] + diff;
+    }
+  }
+}
+
+// staged weight matrix `k` (rows x anything), fake-quantised when config 5 is on and the module is one of
+// the 12 the reference replaces (every caller of this helper is)
+int get_w(vasr_handle* h, const std::string& k, int64_t numel, int64_t rows, std::vector<float>* out) {
+  const std::vector<float>* v;
+  RET(need(h, k, numel, &v));
+  *out = *v;
+  if (h->quant) fake_quant_rows(*out, rows);
+  return VASR_OK;
+}
+int up_w(vasr_handle* h, const std::string& k, int64_t numel, int64_t rows, float** dst) {
+  std::vector<float> w;
+  RET(get_w(h, k, numel, rows, &w));
+  return upload(h, w.data(), w.size(), dst);
 }
 
 int pack_block(vasr_handle* h, const std::string& p, int N, BlockW* w) {
@@ -310,6 +365,7 @@ void default_filterbank(int n_mels, std::vector<float>& fb) {
 }
 
 int pack_frontend_impl(vasr_handle* h);
+int setup_qsites(vasr_handle* h);
 void free_splits(vasr_handle* h);
 int pack_frontend(vasr_handle* h) {
   CK(cudaDeviceSynchronize());
@@ -414,6 +470,25 @@ int split_of(vasr_handle* h, const float* W, int64_t numel, cudaStream_t s, cons
   return VASR_OK;
 }
 
+int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s);
+// Calibration of the output FakeQuantize nodes of one projection: the reference's FakeQuantize in training
+// mode takes min / max of the tensor it is about to quantise (quantize.py:86-88, 99-121), i.e. of the module's
+// own fp32 output given already-quantised inputs.  Probe = the same projection without quantisation,
+// activation, positional encoding or residual, into scratch; then min / max per module and the new scales.
+int calibrate_site(vasr_handle* h, const GemmArgs& g, const QSite& q, float* scratch, cudaStream_t s) {
+  GemmArgs p = g;
+  p.C = scratch; p.ldc = g.N;
+  p.q_scale = p.q_zp = nullptr;
+  p.act = ACT_NONE; p.act_from = 0;
+  p.resid = nullptr; p.pe_time = p.pe_freq = nullptr;
+  RET(gemm(h, p, s));
+  for (int i = 0; i < q.nmod; ++i) {
+    KL(launch_minmax(scratch, g.N, g.M, q.c0[i], q.nc[i], h->q_mm, s, &h->launches));
+    KL(launch_set_qparams(h->q_mm, q.qs, q.qz, q.c0[i], q.nc[i], s, &h->launches));
+  }
+  return VASR_OK;
+}
+
 int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
   if (h->use_tc && (!g.blocked_sum || h->dft_tc)) {
     RET(split_of(h, g.W, g.N * g.K, s, &g.W_split));
@@ -429,13 +504,24 @@ int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
   return VASR_OK;
 }
 
+// site >= 0: the projection hosts quantised modules (only meaningful while quant_active)
+int gemm_q(vasr_handle* h, GemmArgs& g, int site, float* qscratch, cudaStream_t s) {
+  if (site >= 0 && h->quant_active) {
+    const QSite& q = h->qsite[site];
+    g.q_scale = q.qs;
+    g.q_zp = q.qz;
+    if (h->calibrating) RET(calibrate_site(h, g, q, qscratch, s));
+  }
+  return gemm(h, g, s);
+}
+
 int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const float* bias, float* C, int64_t ldc,
            int64_t M, int64_t K, int64_t N, int act, int act_from, const float* resid, int64_t ldr,
-           cudaStream_t s) {
+           cudaStream_t s, int site = -1, float* qscratch = nullptr) {
   GemmArgs g;
   g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = act_from; g.resid = resid; g.ldr = ldr;
-  return gemm(h, g, s);
+  return gemm_q(h, g, site, qscratch, s);
 }
 
 
@@ -490,28 +576,28 @@ int quirk_for(const vasr_handle* h, int stack, int scan_mode) {
 int run_global_context(vasr_handle* h, const Dims& q, const Work& k, cudaStream_t s) {
   const int d = q.d, att = q.att;
   KL(launch_adaptive_pool(k.cat, 2 * d, k.gb, q.B, q.L, q.K1, d, s, &h->launches));
-  RET(linear(h, k.gb, d, h->p1_w, h->p1_b, k.ga, d, q.Mg, d, d, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.gb, d, h->p1_w, h->p1_b, k.ga, d, q.Mg, d, d, ACT_NONE, 0, nullptr, 0, s, Q_P1, k.qscratch));
   for (size_t i = 0; i < h->global.size(); ++i)
     RET(run_block(h, h->global[i], k, k.ga, k.gb, q.B, q.K1, quirk_for(h, 1, -1), s));
   KL(launch_layer_norm(k.ga, d, k.ga, d, h->glo_g, h->glo_b, q.Mg, d, s, &h->launches));
   KL(launch_adaptive_pool(k.ga, d, k.g2, q.B, q.K1, q.K2, d, s, &h->launches));
-  RET(linear(h, k.g2, d, h->p2_w, h->p2_b, k.g2n, d, q.M2, d, d, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.g2, d, h->p2_w, h->p2_b, k.g2n, d, q.M2, d, d, ACT_NONE, 0, nullptr, 0, s, Q_P2, k.qscratch));
   KL(launch_layer_norm(k.g2n, d, k.g2n, d, h->n1_g, h->n1_b, q.M2, d, s, &h->launches));
-  RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s, Q_KV, k.qscratch));
   KL(launch_layer_norm(k.cat, 2 * d, k.u, d, h->n2_g, h->n2_b, q.M, d, s, &h->launches));
-  RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s, Q_Q, k.qscratch));
   KL(launch_attention(k.qb, att, k.kv, k.ob, att, q.B, q.L, q.K2, h->cfg.attention_heads,
                       att / h->cfg.attention_heads, s, &h->launches));
-  RET(linear(h, k.ob, att, h->w_o, h->b_o, k.cat + d, 2 * d, q.M, att, d, ACT_NONE, 0, nullptr, 0, s));
-  RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.ob, att, h->w_o, h->b_o, k.cat + d, 2 * d, q.M, att, d, ACT_NONE, 0, nullptr, 0, s, Q_O, k.qscratch));
+  RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s, Q_F3, k.qscratch));
   KL(launch_gate_mix(k.f3, k.fm, q.M, d, s, &h->launches));
-  RET(linear(h, k.fm, d, h->w_fo, h->b_fo, k.fused, d, q.M, d, d, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.fm, d, h->w_fo, h->b_fo, k.fused, d, q.M, d, d, ACT_NONE, 0, nullptr, 0, s, Q_FO, k.qscratch));
   return VASR_OK;
 }
 
 int run_ctc_head(vasr_handle* h, const Dims& q, const Work& k, const float* x, float* logits, cudaStream_t s) {
   KL(launch_layer_norm(x, q.d, k.u, q.d, h->ctc_g, h->ctc_b, q.M, q.d, s, &h->launches));
-  RET(linear(h, k.u, q.d, h->w_ctc, h->b_ctc, logits, q.V, q.M, q.d, q.V, ACT_NONE, 0, nullptr, 0, s));
+  RET(linear(h, k.u, q.d, h->w_ctc, h->b_ctc, logits, q.V, q.M, q.d, q.V, ACT_NONE, 0, nullptr, 0, s, Q_CTC, k.qscratch));
   return VASR_OK;
 }
 
@@ -528,7 +614,7 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
   g.M = q.M; g.N = d; g.K = 3 * q.n_mels;
   g.act = ACT_GELU; g.act_from = 0;
   g.pe_time = h->pe_time; g.pe_freq = h->pe_freq; g.pe_half = d / 2; g.pe_rows = q.L;
-  RET(gemm(h, g, s));
+  RET(gemm_q(h, g, Q_TB, k.qscratch, s));
   KL(launch_layer_norm(k.xa, d, k.xa, d, h->tb_g, h->tb_bt, q.M, d, s, &h->launches));
   if (f_tb) CK(cudaMemcpyAsync(f_tb, k.xa, (size_t)q.M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
   for (size_t i = 0; i < h->local.size(); ++i)
@@ -585,6 +671,54 @@ void timing_begin(vasr_handle* h, cudaStream_t s) {
 }
 void timing_end(vasr_handle* h, cudaStream_t s) {
   if (h->timing) cudaEventRecord(h->ev_t1, s);
+}
+
+// the nine projections that host the twelve quantised modules, with their column ranges
+int setup_qsites(vasr_handle* h) {
+  const int d = h->cfg.d_model, att = h->cfg.attention_dim, V = h->cfg.vocab_size;
+  auto site = [&](int id, int N, std::initializer_list<const char*> names, std::initializer_list<int> widths) {
+    QSite& q = h->qsite[id];
+    q.N = N;
+    q.nmod = 0;
+    int c = 0;
+    auto w = widths.begin();
+    for (const char* nm : names) {
+      q.name[q.nmod] = nm; q.c0[q.nmod] = c; q.nc[q.nmod] = *w;
+      c += *w; ++w; ++q.nmod;
+    }
+  };
+  site(Q_TB, d, {"temporal_binding.conv"}, {d});
+  site(Q_P1, d, {"global_context.pool1.pool_proj"}, {d});
+  site(Q_P2, d, {"global_context.pool2.pool_proj"}, {d});
+  site(Q_Q, att, {"global_context.cross_attention.q_proj"}, {att});
+  site(Q_KV, 2 * att, {"global_context.cross_attention.k_proj", "global_context.cross_attention.v_proj"}, {att, att});
+  site(Q_O, d, {"global_context.cross_attention.out_proj"}, {d});
+  site(Q_F3, 3 * d, {"global_context.fusion.gate_proj.0", "global_context.fusion.local_proj",
+                     "global_context.fusion.global_proj"}, {d, d, d});
+  site(Q_FO, d, {"global_context.fusion.out_proj"}, {d});
+  site(Q_CTC, V, {"ctc_head.proj.2"}, {V});
+  for (int i = 0; i < Q_SITES; ++i) {
+    QSite& q = h->qsite[i];
+    std::vector<float> zeros((size_t)q.N, 0.f);     // scale 0 = pass-through until calibrated (quantize.py:82-84)
+    RET(upload(h, zeros.data(), zeros.size(), &q.qs));
+    RET(upload(h, zeros.data(), zeros.size(), &q.qz));
+  }
+  if (!h->q_mm) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, 2 * sizeof(float)));
+    h->q_mm = static_cast<float*>(p);
+  }
+  return VASR_OK;
+}
+
+QSite* find_module(vasr_handle* h, const char* module, int* idx) {
+  for (int i = 0; i < Q_SITES; ++i)
+    for (int j = 0; j < h->qsite[i].nmod; ++j)
+      if (strcmp(h->qsite[i].name[j], module) == 0) {
+        *idx = j;
+        return &h->qsite[i];
+      }
+  return nullptr;
 }
 
 }  // namespace
@@ -649,6 +783,7 @@ void vasr_destroy(vasr_handle* h) {
   free_weights(h);
   for (void* p : h->frontend_allocs) cudaFree(p);
   if (h->ws.base) cudaFree(h->ws.base);
+  if (h->q_mm) cudaFree(h->q_mm);
   for (auto& e : h->ev) cudaEventDestroy(e);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -680,8 +815,9 @@ int vasr_commit_weights(vasr_handle* h) {
   const vasr_config& c = h->cfg;
   const int d = c.d_model, di = d * c.ssm_expand_ratio, nm = c.mel_bins, att = c.attention_dim;
   // temporal binding: conv.weight (d, mel, 3) -> (d, 3*mel) with k index = tap*mel + channel
-  const std::vector<float>* cw;
-  RET(need(h, "temporal_binding.conv.weight", (int64_t)d * nm * 3, &cw));
+  std::vector<float> cwv;
+  RET(get_w(h, "temporal_binding.conv.weight", (int64_t)d * nm * 3, d, &cwv));
+  const std::vector<float>* cw = &cwv;
   std::vector<float> tbw((size_t)d * 3 * nm);
   for (int o = 0; o < d; ++o)
     for (int ch = 0; ch < nm; ++ch)
@@ -707,37 +843,41 @@ int vasr_commit_weights(vasr_handle* h) {
     RET(pack_block(h, gc + "global_ssm.layers." + std::to_string(i) + ".", c.global_ssm_state_dim, &h->global[i]));
   RET(up(h, gc + "global_ssm.norm.weight", d, &h->glo_g));
   RET(up(h, gc + "global_ssm.norm.bias", d, &h->glo_b));
-  RET(up(h, gc + "pool1.pool_proj.weight", (int64_t)d * d, &h->p1_w));
+  RET(up_w(h, gc + "pool1.pool_proj.weight", (int64_t)d * d, d, &h->p1_w));
   RET(up(h, gc + "pool1.pool_proj.bias", d, &h->p1_b));
-  RET(up(h, gc + "pool2.pool_proj.weight", (int64_t)d * d, &h->p2_w));
+  RET(up_w(h, gc + "pool2.pool_proj.weight", (int64_t)d * d, d, &h->p2_w));
   RET(up(h, gc + "pool2.pool_proj.bias", d, &h->p2_b));
   RET(up(h, gc + "norm1.weight", d, &h->n1_g));
   RET(up(h, gc + "norm1.bias", d, &h->n1_b));
   RET(up(h, gc + "norm2.weight", d, &h->n2_g));
   RET(up(h, gc + "norm2.bias", d, &h->n2_b));
-  RET(up(h, gc + "cross_attention.q_proj.weight", (int64_t)att * d, &h->w_q));
+  RET(up_w(h, gc + "cross_attention.q_proj.weight", (int64_t)att * d, att, &h->w_q));
   RET(up(h, gc + "cross_attention.q_proj.bias", att, &h->b_q));
-  const std::vector<float>*kw, *kb, *vw, *vb;
-  RET(need(h, gc + "cross_attention.k_proj.weight", (int64_t)att * d, &kw));
+  const std::vector<float>*kb, *vb;
+  std::vector<float> kwv, vwv;
+  RET(get_w(h, gc + "cross_attention.k_proj.weight", (int64_t)att * d, att, &kwv));
   RET(need(h, gc + "cross_attention.k_proj.bias", att, &kb));
-  RET(need(h, gc + "cross_attention.v_proj.weight", (int64_t)att * d, &vw));
+  RET(get_w(h, gc + "cross_attention.v_proj.weight", (int64_t)att * d, att, &vwv));
   RET(need(h, gc + "cross_attention.v_proj.bias", att, &vb));
+  const std::vector<float>*kw = &kwv, *vw = &vwv;
   std::vector<float> wkv(*kw), bkv(*kb);
   wkv.insert(wkv.end(), vw->begin(), vw->end());
   bkv.insert(bkv.end(), vb->begin(), vb->end());
   RET(upload(h, wkv.data(), wkv.size(), &h->w_kv));
   RET(upload(h, bkv.data(), bkv.size(), &h->b_kv));
-  RET(up(h, gc + "cross_attention.out_proj.weight", (int64_t)d * att, &h->w_o));
+  RET(up_w(h, gc + "cross_attention.out_proj.weight", (int64_t)d * att, d, &h->w_o));
   RET(up(h, gc + "cross_attention.out_proj.bias", d, &h->b_o));
   // fusion: one (3d x 2d) projection of [local | ctx]: gate rows, then local_proj on the left
   // half, then global_proj on the right half (zeros elsewhere).
-  const std::vector<float>*gw, *gb, *lw, *lb, *cw2, *cb2;
-  RET(need(h, gc + "fusion.gate_proj.0.weight", (int64_t)d * 2 * d, &gw));
+  const std::vector<float>*gb, *lb, *cb2;
+  std::vector<float> gwv, lwv, cwv2;
+  RET(get_w(h, gc + "fusion.gate_proj.0.weight", (int64_t)d * 2 * d, d, &gwv));
   RET(need(h, gc + "fusion.gate_proj.0.bias", d, &gb));
-  RET(need(h, gc + "fusion.local_proj.weight", (int64_t)d * d, &lw));
+  RET(get_w(h, gc + "fusion.local_proj.weight", (int64_t)d * d, d, &lwv));
   RET(need(h, gc + "fusion.local_proj.bias", d, &lb));
-  RET(need(h, gc + "fusion.global_proj.weight", (int64_t)d * d, &cw2));
+  RET(get_w(h, gc + "fusion.global_proj.weight", (int64_t)d * d, d, &cwv2));
   RET(need(h, gc + "fusion.global_proj.bias", d, &cb2));
+  const std::vector<float>*gw = &gwv, *lw = &lwv, *cw2 = &cwv2;
   std::vector<float> wf3((size_t)3 * d * 2 * d, 0.f), bf3;
   memcpy(wf3.data(), gw->data(), gw->size() * sizeof(float));
   for (int o = 0; o < d; ++o) {
@@ -749,12 +889,14 @@ int vasr_commit_weights(vasr_handle* h) {
   bf3.insert(bf3.end(), cb2->begin(), cb2->end());
   RET(upload(h, wf3.data(), wf3.size(), &h->w_f3));
   RET(upload(h, bf3.data(), bf3.size(), &h->b_f3));
-  RET(up(h, gc + "fusion.out_proj.weight", (int64_t)d * d, &h->w_fo));
+  RET(up_w(h, gc + "fusion.out_proj.weight", (int64_t)d * d, d, &h->w_fo));
   RET(up(h, gc + "fusion.out_proj.bias", d, &h->b_fo));
   RET(up(h, "ctc_head.proj.0.weight", d, &h->ctc_g));
   RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
-  RET(up(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &h->w_ctc));
+  RET(up_w(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, c.vocab_size, &h->w_ctc));
   RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
+  h->quant_active = h->quant;
+  if (h->quant_active) RET(setup_qsites(h));
   h->committed = true;
   return VASR_OK;
 }
@@ -925,6 +1067,58 @@ int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float
   g.A = x_dev; g.lda = ldx; g.W = w_dev; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
   KL(launch_gemm(g, static_cast<cudaStream_t>(stream), nullptr));
+  return VASR_OK;
+}
+
+int vasr_set_quantization(vasr_handle* h, int enabled) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  if ((enabled != 0) != (h->quant != 0)) {
+    h->quant = enabled != 0;
+    h->committed = false;      // weights are re-packed (fake-quantised or not) at the next commit
+  }
+  return VASR_OK;
+}
+
+int vasr_calibrate(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, void* stream) {
+  RET(check_ready(h));
+  if (!h->quant_active) return fail(VASR_ERR_STATE, "quantisation is not enabled (vasr_set_quantization + commit)");
+  if (B <= 0 || T < 1 || !mel_dev) return fail(VASR_ERR_INVALID, "null argument");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims q = make_dims(h, B, 0, T);
+  Work k;
+  RET(ensure_workspace(h, q, false, true, &k));
+  KL(launch_mel_finish(mel_dev, nullptr, nullptr, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches));
+  h->calibrating = 1;
+  const int r = run_model(h, q, k, k.logits, nullptr, nullptr, nullptr, s);
+  h->calibrating = 0;
+  return r;
+}
+
+int vasr_get_quant_params(vasr_handle* h, const char* module, float* scale, float* zero_point) {
+  if (!h || !module || !scale || !zero_point) return fail(VASR_ERR_INVALID, "null argument");
+  if (!h->quant_active) return fail(VASR_ERR_STATE, "quantisation is not enabled");
+  int j = 0;
+  QSite* q = find_module(h, module, &j);
+  if (!q) return fail(VASR_ERR_INVALID, std::string("not a quantised module: ") + module);
+  RET(bind_device(h));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(scale, q->qs + q->c0[j], sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(zero_point, q->qz + q->c0[j], sizeof(float), cudaMemcpyDeviceToHost));
+  return VASR_OK;
+}
+
+int vasr_set_quant_params(vasr_handle* h, const char* module, float scale, float zero_point) {
+  if (!h || !module) return fail(VASR_ERR_INVALID, "null argument");
+  if (!h->quant_active) return fail(VASR_ERR_STATE, "quantisation is not enabled");
+  int j = 0;
+  QSite* q = find_module(h, module, &j);
+  if (!q) return fail(VASR_ERR_INVALID, std::string("not a quantised module: ") + module);
+  RET(bind_device(h));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> sv((size_t)q->nc[j], scale), zv((size_t)q->nc[j], zero_point);
+  CK(cudaMemcpy(q->qs + q->c0[j], sv.data(), sv.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(q->qz + q->c0[j], zv.data(), zv.size() * sizeof(float), cudaMemcpyHostToDevice));
   return VASR_OK;
 }
 

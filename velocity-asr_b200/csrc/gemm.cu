@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256, BLOCKED ? 1 : 2) gemm_tn_kernel(GemmArgs 
     for (int j = 0; j < 4; ++j) {
       const int64_t n = nbase + j;
       float x = hsum2(acc[i][j]) + bias[j];
+      if (g.q_scale && n < g.N) x = fake_quant_u8(x, g.q_scale[n], g.q_zp[n]);
       if (n >= g.act_from) x = apply_act(x, g.act);
       if (g.pe_time) {
         if (n < g.pe_half) {

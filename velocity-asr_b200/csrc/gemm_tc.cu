@@ -189,6 +189,8 @@ struct TcArgs {
   float* C;
   int64_t ldc;
   const float* bias;
+  const float* q_scale;
+  const float* q_zp;
   int act_from;
   const float* resid;
   int64_t ldr;
@@ -212,7 +214,7 @@ __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
 }
 
-template <int ACT, bool PE, bool RESID>
+template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
@@ -410,6 +412,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool col_ok = n < g.N;                     // N % 4 == 0: the group is valid or not as a whole
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
         if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        float4 qs4 = make_float4(0.f, 0.f, 0.f, 0.f), qz4 = qs4;
+        if (QUANT && col_ok) {
+          qs4 = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
+          qz4 = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
+        }
         if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
         const bool act_on = ACT != ACT_NONE && n >= g.act_from;
 #pragma unroll
@@ -420,6 +427,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!col_ok || mi >= g.rows_per_batch) continue;
           const int64_t m = batch * g.rows_per_batch + mi;
           x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (QUANT) {
+            x.x = fake_quant_u8(x.x, qs4.x, qz4.x); x.y = fake_quant_u8(x.y, qs4.y, qz4.y);
+            x.z = fake_quant_u8(x.z, qs4.z, qz4.z); x.w = fake_quant_u8(x.w, qs4.w, qz4.w);
+          }
           if (act_on) {
             x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
             x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
@@ -529,7 +540,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int ACT, bool PE, bool RESID>
+template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                 const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
@@ -732,6 +743,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool col_ok = n < g.N;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
         if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        float4 qs4 = make_float4(0.f, 0.f, 0.f, 0.f), qz4 = qs4;
+        if (QUANT && col_ok) {
+          qs4 = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
+          qz4 = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
+        }
         if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
         const bool act_on = ACT != ACT_NONE && n >= g.act_from;
 #pragma unroll
@@ -742,6 +758,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (!col_ok || mi >= g.rows_per_batch) continue;
           const int64_t m = batch * g.rows_per_batch + mi;
           x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (QUANT) {
+            x.x = fake_quant_u8(x.x, qs4.x, qz4.x); x.y = fake_quant_u8(x.y, qs4.y, qz4.y);
+            x.z = fake_quant_u8(x.z, qs4.z, qz4.z); x.w = fake_quant_u8(x.w, qs4.w, qz4.w);
+          }
           if (act_on) {
             x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
             x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
@@ -826,6 +846,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
   // the epilogue moves 16-byte groups of four columns
   if ((g.N & 3) || (g.ldc & 3) || !al16(g.C) || (g.act_from & 3)) return false;
   if (g.bias && !al16(g.bias)) return false;
+  if (g.q_scale && (!g.q_zp || !al16(g.q_scale) || !al16(g.q_zp))) return false;
   if (g.resid && ((g.ldr & 3) || !al16(g.resid))) return false;
   if (g.pe_time && ((g.pe_half & 3) || !al16(g.pe_time) || !al16(g.pe_freq))) return false;
   return true;
@@ -873,6 +894,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.m_tiles_per_batch = (int)((rpb + (pair ? 2 : 1) * TBM - 1) / ((pair ? 2 : 1) * TBM));
   a.n_tiles = (int)((g.N + TBN - 1) / TBN);
   a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act_from = g.act_from;
+  a.q_scale = g.q_scale; a.q_zp = g.q_zp;
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
   a.trace = g_trace;
@@ -892,18 +914,29 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (err == cudaSuccess) kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
   };
+  const bool quant = g.q_scale != nullptr;
+  if (quant) {   // config 5: the quantised modules are plain projections, or the temporal-binding conv (GELU + pos-enc)
+    if (rs || !((g.act == ACT_NONE && !pe) || (g.act == ACT_GELU && pe))) return cudaErrorNotSupported;
+    if (pair) {
+      if (pe) go2(gemm_tc2_kernel<ACT_GELU, true, false, true>);
+      else go2(gemm_tc2_kernel<ACT_NONE, false, false, true>);
+    } else {
+      if (pe) go1(gemm_tc_kernel<ACT_GELU, true, false, true>);
+      else go1(gemm_tc_kernel<ACT_NONE, false, false, true>);
+    }
+  }
 #define VASR_TC_CASE(ACTV)                                                                   \
-  if (g.act == ACTV) {                                                                       \
+  if (!quant && g.act == ACTV) {                                                             \
     if (pair) {                                                                              \
-      if (pe && rs) go2(gemm_tc2_kernel<ACTV, true, true>);                                  \
-      else if (pe) go2(gemm_tc2_kernel<ACTV, true, false>);                                  \
-      else if (rs) go2(gemm_tc2_kernel<ACTV, false, true>);                                  \
-      else go2(gemm_tc2_kernel<ACTV, false, false>);                                         \
+      if (pe && rs) go2(gemm_tc2_kernel<ACTV, true, true, false>);                           \
+      else if (pe) go2(gemm_tc2_kernel<ACTV, true, false, false>);                           \
+      else if (rs) go2(gemm_tc2_kernel<ACTV, false, true, false>);                           \
+      else go2(gemm_tc2_kernel<ACTV, false, false, false>);                                  \
     } else {                                                                                 \
-      if (pe && rs) go1(gemm_tc_kernel<ACTV, true, true>);                                   \
-      else if (pe) go1(gemm_tc_kernel<ACTV, true, false>);                                   \
-      else if (rs) go1(gemm_tc_kernel<ACTV, false, true>);                                   \
-      else go1(gemm_tc_kernel<ACTV, false, false>);                                          \
+      if (pe && rs) go1(gemm_tc_kernel<ACTV, true, true, false>);                            \
+      else if (pe) go1(gemm_tc_kernel<ACTV, true, false, false>);                            \
+      else if (rs) go1(gemm_tc_kernel<ACTV, false, true, false>);                            \
+      else go1(gemm_tc_kernel<ACTV, false, false, false>);                                   \
     }                                                                                        \
   }
   VASR_TC_CASE(ACT_NONE)

@@ -10,7 +10,8 @@ namespace vasr {
 // C[m, n] = epi( sum_k A[m, k] * W[n, k] ), A rows K-contiguous, W (N, K) as nn.Linear stores it.
 // Row m of A lives at A + (m / rows_per_batch) * batch_stride + (m % rows_per_batch) * lda,
 // which lets a strided / overlapping view (conv frames, STFT frames) be used without im2col.
-// Epilogue, in order: + bias[n]; act on columns n >= act_from; + pos-enc (time table row
+// Epilogue, in order: + bias[n]; FakeQuantize with per-column (q_scale[n], q_zp[n]) when given (config 5);
+// act on columns n >= act_from; + pos-enc (time table row
 // m % pe_rows for n < pe_half, learned freq vector for n >= pe_half); + resid[m, n].
 struct GemmArgs {
   const float* A = nullptr;
@@ -20,6 +21,8 @@ struct GemmArgs {
   const float* W = nullptr;
   const float* W_split = nullptr;  // [rna_tf32(W) | rna_tf32(W - hi)], 2*N*K floats (launch_split_tf32); tensor-core path only
   const float* bias = nullptr;
+  const float* q_scale = nullptr;  // (N) device; with q_zp: output FakeQuantize per column (scale <= 0: none)
+  const float* q_zp = nullptr;
   float* C = nullptr;
   int64_t ldc = 0;
   int64_t M = 0, N = 0, K = 0;
@@ -40,6 +43,15 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
 // hl[0..n) = rna_tf32(w), hl[n..2n) = rna_tf32(w - hl[0..n)): the weight operand of launch_gemm_tc.
 cudaError_t launch_split_tf32(const float* w, float* hl, int64_t n, cudaStream_t s);
 extern long long* g_trace;   // debug: device buffer (5 x 128 clock64 slots) CTA 0 of the projection kernel writes
+
+// ---------------------------------------------------------------- quantisation (config 5) ---
+// mm[0] = min, mm[1] = max over x[m, c0 .. c0+nc) for m < M (row stride ldx).  Deterministic (one CTA).
+cudaError_t launch_minmax(const float* x, int64_t ldx, int64_t M, int c0, int nc, float* mm, cudaStream_t s,
+                          int64_t* launches);
+// FakeQuantize._update_scale_zp for an asymmetric per-tensor uint8 node (quantize.py:116-121):
+// scale = max((max - min) / 255, 1e-10), zp = 0 - min / scale, written to q_scale/q_zp[c0 .. c0+nc).
+cudaError_t launch_set_qparams(const float* mm, float* q_scale, float* q_zp, int c0, int nc, cudaStream_t s,
+                               int64_t* launches);
 
 // ---------------------------------------------------------------- normalisation / conv ---
 // y[m, :] = LayerNorm(x[m, :]) * gamma + beta over C channels (eps 1e-5, biased variance).

@@ -14,6 +14,7 @@ from .engine import VELOCITYASR
 from .frontend import compute_mel_spectrogram, SAMPLE_RATE, N_FFT, HOP_LENGTH, N_MELS
 from .ctc import ctc_greedy_decode, CTCDecoder, create_default_vocabulary, BLANK_TOKEN
 from .ops import selective_scan, selective_scan_fn, linear, split_tf32
+from .quantize import QuantizationConfig, prepare_model_for_qat, calibrate_model
 
 MAMBA_AVAILABLE = True  # scan_mode="mamba" is served by the in-tree scan kernel (ssm.py:20-26)
 
@@ -28,4 +29,5 @@ __all__ = [
     "compute_mel_spectrogram", "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "N_MELS",
     "ctc_greedy_decode", "CTCDecoder", "create_default_vocabulary", "BLANK_TOKEN",
     "selective_scan", "selective_scan_fn", "linear", "split_tf32", "MAMBA_AVAILABLE", "SCAN_MODES",
+    "QuantizationConfig", "prepare_model_for_qat", "calibrate_model",
 ]

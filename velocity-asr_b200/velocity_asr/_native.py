@@ -40,6 +40,10 @@ _SIGNATURES = {
     "vasr_transcribe_host": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "vasr_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                             c_int, c_void_p]),
+    "vasr_set_quantization": (c_int, [c_void_p, c_int]),
+    "vasr_calibrate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "vasr_get_quant_params": (c_int, [c_void_p, c_char_p, POINTER(c_float), POINTER(c_float)]),
+    "vasr_set_quant_params": (c_int, [c_void_p, c_char_p, c_float, c_float]),
     "vasr_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                c_int64, c_int, c_void_p]),

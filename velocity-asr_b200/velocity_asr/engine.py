@@ -48,14 +48,18 @@ class _Engine:
         except Exception:
             pass
 
-    def sync_weights(self, state: Dict[str, torch.Tensor], extra: Dict[str, torch.Tensor]):
-        fp = tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
+    def sync_weights(self, state: Dict[str, torch.Tensor], extra: Dict[str, torch.Tensor], quantized: bool = False,
+                     act_qparams: Optional[Dict[str, Tuple[float, float]]] = None):
+        fp = (quantized,) + tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
         if fp == self.fingerprint:
             return
+        _native.check(self.lib.vasr_set_quantization(self.handle, int(quantized)))
         for k, v in list(state.items()) + list(extra.items()):
             host = v.detach().to("cpu", torch.float32).contiguous()
             _native.check(self.lib.vasr_set_weight(self.handle, k.encode(), _native.ptr(host), host.numel()))
         _native.check(self.lib.vasr_commit_weights(self.handle))
+        for name, (scale, zp) in ((act_qparams or {}) if quantized else {}).items():   # calibration survives a re-commit
+            _native.check(self.lib.vasr_set_quant_params(self.handle, name.encode(), scale, zp))
         self.fingerprint = fp
 
 
@@ -101,7 +105,8 @@ class VELOCITYASR(nn.Module):
         # same keys and order as state_dict(), without the detach/copy work of building one per call
         state = dict(self.named_parameters())
         state.update({k: v for k, v in self.named_buffers() if k.split(".")[-1] not in self._non_persistent})
-        eng.sync_weights(state, {"frontend.mel_filterbank": fb, "frontend.window": win})
+        eng.sync_weights(state, {"frontend.mel_filterbank": fb, "frontend.window": win},
+                         quantized=getattr(self, "_quantized", False), act_qparams=getattr(self, "_act_qparams", None))
         return eng
 
     @property
