@@ -118,6 +118,13 @@ int vasr_selective_scan(const float* x, int64_t ldx, const float* dt, int64_t ld
 int vasr_ctc_greedy(const float* logits_dev, int64_t B, int64_t L, int64_t V, int blank, int collapse,
                     int32_t* tokens_dev, int32_t* lens_dev, void* stream);
 
+/* ---- ctc_greedy_decode_with_timestamps (velocity_asr/decode.py:74-125)
+ * As above with repeats collapsed, plus per token the [start, end) frame range of its run of equal
+ * predictions: tokens / starts / ends (B, L) int32 left-packed, lens (B). */
+int vasr_ctc_greedy_timestamps(const float* logits_dev, int64_t B, int64_t L, int64_t V, int blank,
+                               int32_t* tokens_dev, int32_t* starts_dev, int32_t* ends_dev, int32_t* lens_dev,
+                               void* stream);
+
 /* ---- transcribe: load -> mel -> model -> greedy (scripts/transcribe.py:69-82), batched.
  * tokens (B, L) int32, lens (B); L = vasr_num_tokens(vasr_num_frames(S)). */
 int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S,

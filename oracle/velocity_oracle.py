@@ -530,6 +530,30 @@ def ctc_greedy_decode(logits, blank_token: int = BLANK_TOKEN, collapse_repeated:
     return [collapse_tokens(row, blank_token, collapse_repeated) for row in pred]
 
 
+def ctc_greedy_decode_with_timestamps(logits, blank_token: int = BLANK_TOKEN):
+    """decode.py:74-125, loop restated: (tokens, [(start_frame, end_frame)]) per utterance."""
+    out = []
+    for pred in np.argmax(np.asarray(logits), axis=-1):
+        tokens, stamps, prev, start = [], [], None, 0
+        for i, tok in enumerate(pred):
+            tok = int(tok)
+            if tok == blank_token:
+                if prev is not None and prev != blank_token:
+                    stamps.append((start, i))
+                prev = tok
+                continue
+            if tok != prev:
+                if prev is not None and prev != blank_token:
+                    stamps.append((start, i))
+                tokens.append(tok)
+                start = i
+            prev = tok
+        if prev is not None and prev != blank_token:
+            stamps.append((start, len(pred)))
+        out.append((tokens, stamps))
+    return out
+
+
 def transcribe(audio, sd, cfg=None, dtype=np.float64) -> List[List[int]]:
     """load->mel->model->greedy, the order of scripts/transcribe.py:69-82."""
     return ctc_greedy_decode(forward(log_mel(audio, dtype=dtype), sd, cfg, dtype))

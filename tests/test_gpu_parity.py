@@ -378,6 +378,24 @@ def test_ctc_greedy_known_answers(va, golden):
     assert dec.decode_greedy(lg) == ["ab c"]
 
 
+def test_ctc_timestamps_vs_oracle(va):
+    """ctc_greedy_decode_with_timestamps (decode.py:74-125): bit-exact tokens and frame ranges."""
+    rs = np.random.RandomState(3)
+    # few classes + a strong blank prior -> long runs, repeats across blanks, runs touching both ends
+    for (B, L, V) in [(5, 97, 6), (3, 1, 4), (2, 300, 3), (1, 33, 2)]:
+        lg = rs.standard_normal((B, L, V)).astype(np.float32)
+        lg[..., 0] += 0.8
+        lg = np.repeat(lg, 2, axis=1)[:, :L]          # duplicate frames: runs of >= 2
+        got = va.ctc_greedy_decode_with_timestamps(torch.from_numpy(lg).cuda())
+        assert got == O.ctc_greedy_decode_with_timestamps(lg)
+        assert [t for t, _ in got] == va.ctc_greedy_decode(torch.from_numpy(lg).cuda())
+    known = np.full((1, 13, 8), -5.0, np.float32)
+    for i, t in enumerate([0, 5, 5, 0, 5, 7, 7, 7, 0, 0, 3, 3, 5]):
+        known[0, i, t] = 5.0
+    assert va.ctc_greedy_decode_with_timestamps(torch.from_numpy(known).cuda()) == \
+        [([5, 5, 7, 3, 5], [(1, 3), (4, 5), (5, 8), (10, 12), (12, 13)])]
+
+
 def test_ctc_greedy_random_vs_oracle(va):
     g = torch.Generator().manual_seed(4)
     pred = torch.randint(0, 4, (7, 1003), generator=g)           # many blanks and repeats, ragged outputs

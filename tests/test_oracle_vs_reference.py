@@ -56,3 +56,14 @@ def test_yaml_mapping_matches_reference_defaults():
               "global_ssm_layers", "global_ssm_state_dim", "attention_heads", "attention_dim", "vocab_size",
               "scan_mode", "dropout"):
         assert getattr(c, f) == getattr(r, f), f
+
+
+def test_timestamp_decode_matches_reference():
+    """decode.py:74-125 against the oracle's restatement, on run-heavy random predictions."""
+    rs = np.random.RandomState(3)
+    for (B, L, V) in [(5, 97, 6), (3, 1, 4), (2, 300, 3), (1, 33, 2)]:
+        lg = rs.standard_normal((B, L, V)).astype(np.float32)
+        lg[..., 0] += 0.8
+        lg = np.repeat(lg, 2, axis=1)[:, :L]
+        ref = R.decode.ctc_greedy_decode_with_timestamps(torch.from_numpy(lg))
+        assert [(list(t), [tuple(x) for x in s]) for t, s in ref] == O.ctc_greedy_decode_with_timestamps(lg)

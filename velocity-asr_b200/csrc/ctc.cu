@@ -64,7 +64,53 @@ __global__ void __launch_bounds__(32) ctc_collapse_kernel(const int32_t* __restr
   if (lane == 0) lens[b] = count;
 }
 
+// ctc_greedy_decode_with_timestamps (decode.py:74-125): a token is emitted where a run of equal non-blank
+// predictions starts, its (start, end) are the first frame of the run and the first frame after it.  Run
+// starts and run ends come in the same order, so both are compacted with the same ballot / popc ranks.
+__global__ void __launch_bounds__(32) ctc_runs_kernel(const int32_t* __restrict__ pred, int32_t* __restrict__ tokens,
+                                                      int32_t* __restrict__ starts, int32_t* __restrict__ ends,
+                                                      int32_t* __restrict__ lens, int64_t L, int blank) {
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int32_t* p = pred + b * L;
+  int ns = 0, ne = 0;
+  for (int64_t t0 = 0; t0 < L; t0 += 32) {
+    const int64_t t = t0 + lane;
+    int tok = blank;
+    bool st = false, en = false;
+    if (t < L) {
+      tok = p[t];
+      st = tok != blank && (t == 0 || tok != p[t - 1]);
+      en = tok != blank && (t == L - 1 || tok != p[t + 1]);
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, st), me = __ballot_sync(0xffffffffu, en);
+    const unsigned below = (1u << lane) - 1u;
+    if (st) {
+      const int k = ns + __popc(ms & below);
+      tokens[b * L + k] = tok;
+      starts[b * L + k] = (int32_t)t;
+    }
+    if (en) ends[b * L + ne + __popc(me & below)] = (int32_t)(t + 1);
+    ns += __popc(ms);
+    ne += __popc(me);
+  }
+  for (int64_t t = ns + lane; t < L; t += 32) {
+    tokens[b * L + t] = -1;
+    starts[b * L + t] = -1;
+    ends[b * L + t] = -1;
+  }
+  if (lane == 0) lens[b] = ns;
+}
+
 }  // namespace
+
+cudaError_t launch_ctc_runs(const int32_t* pred, int32_t* tokens, int32_t* starts, int32_t* ends, int32_t* lens,
+                            int64_t B, int64_t L, int blank, cudaStream_t s, int64_t* launches) {
+  if (B <= 0) return cudaSuccess;
+  ctc_runs_kernel<<<(unsigned)B, 32, 0, s>>>(pred, tokens, starts, ends, lens, L, blank);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, cudaStream_t s,
                           int64_t* launches) {

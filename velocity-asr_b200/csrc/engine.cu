@@ -1012,6 +1012,21 @@ int vasr_ctc_greedy(const float* logits_dev, int64_t B, int64_t L, int64_t V, in
   return VASR_OK;
 }
 
+int vasr_ctc_greedy_timestamps(const float* logits_dev, int64_t B, int64_t L, int64_t V, int blank,
+                               int32_t* tokens_dev, int32_t* starts_dev, int32_t* ends_dev, int32_t* lens_dev,
+                               void* stream) {
+  if (!tokens_dev || !starts_dev || !ends_dev || !lens_dev || (!logits_dev && B * L > 0))
+    return fail(VASR_ERR_INVALID, "null argument");
+  if (B <= 0) return VASR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t* pred = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&pred), (size_t)(B * L > 0 ? B * L : 1) * sizeof(int32_t), s));
+  KL(launch_argmax(logits_dev, pred, B * L, (int)V, s, nullptr));
+  KL(launch_ctc_runs(pred, tokens_dev, starts_dev, ends_dev, lens_dev, B, L, blank, s, nullptr));
+  CK(cudaFreeAsync(pred, s));
+  return VASR_OK;
+}
+
 static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pcm_host, int64_t B, int64_t S,
                            int32_t* tokens_dev, int32_t* lens_dev, int32_t* tokens_host, int32_t* lens_host,
                            cudaStream_t s) {

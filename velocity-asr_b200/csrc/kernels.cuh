@@ -123,6 +123,9 @@ cudaError_t launch_gate_mix(const float* f3, float* out, int64_t M, int C, cudaS
 // ---------------------------------------------------------------- CTC greedy ------------
 cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, cudaStream_t s,
                           int64_t* launches);
+// tokens / starts / ends (B, L) left-packed: run starts of equal non-blank predictions, with [start, end) frames
+cudaError_t launch_ctc_runs(const int32_t* pred, int32_t* tokens, int32_t* starts, int32_t* ends, int32_t* lens,
+                            int64_t B, int64_t L, int blank, cudaStream_t s, int64_t* launches);
 cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
                                 int blank, int collapse, cudaStream_t s, int64_t* launches);
 

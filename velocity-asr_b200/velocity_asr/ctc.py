@@ -1,7 +1,7 @@
 """CTC decoding: ctc_greedy_decode / CTCDecoder / create_default_vocabulary of
 velocity_asr/decode.py, with the argmax and the blank/repeat collapse done on the GPU."""
 import ctypes
-from typing import List
+from typing import List, Tuple
 
 import torch
 
@@ -33,6 +33,33 @@ def ctc_greedy_decode(logits: torch.Tensor, blank_token: int = BLANK_TOKEN,
                                           ctypes.c_void_p(torch.cuda.current_stream(lg.device).cuda_stream)))
     tokens, lens = tokens.cpu(), lens.cpu()
     return [tokens[b, : int(lens[b])].tolist() for b in range(B)]
+
+
+def ctc_greedy_decode_with_timestamps(logits: torch.Tensor, blank_token: int = BLANK_TOKEN
+                                      ) -> List[Tuple[List[int], List[Tuple[int, int]]]]:
+    """decode.py:74-125: per utterance (tokens, [(start_frame, end_frame), ...]); a token's range is the run
+    of equal non-blank argmax frames it was collapsed from (end exclusive).  Frame -> seconds is
+    frame * 2 * 160 / 16000 (scripts/transcribe.py:42-45)."""
+    if logits.dim() != 3:
+        raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
+    if logits.device.type != "cuda":
+        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    B, L, V = logits.shape
+    if B == 0:
+        return []
+    if L == 0:
+        return [([], []) for _ in range(B)]
+    lg = logits.to(torch.float32).contiguous()
+    buf = torch.empty(3, B, L, dtype=torch.int32, device=lg.device)
+    lens = torch.empty(B, dtype=torch.int32, device=lg.device)
+    lib = _native.lib()
+    with torch.cuda.device(lg.device):
+        _native.check(lib.vasr_ctc_greedy_timestamps(
+            _native.ptr(lg), B, L, V, int(blank_token), _native.ptr(buf[0]), _native.ptr(buf[1]), _native.ptr(buf[2]),
+            _native.ptr(lens), ctypes.c_void_p(torch.cuda.current_stream(lg.device).cuda_stream)))
+    buf, lens = buf.cpu().numpy(), lens.cpu().tolist()
+    return [(buf[0, b, :n].tolist(), list(zip(buf[1, b, :n].tolist(), buf[2, b, :n].tolist())))
+            for b, n in enumerate(lens)]
 
 
 class CTCDecoder:
