@@ -235,6 +235,28 @@ class VELOCITYASR(nn.Module):
         sl["done"].synchronize()
         return _token_lists(sl["tok_h"], sl["lens_h"])
 
+    @torch.no_grad()
+    def transcribe_list(self, utterances: List[torch.Tensor], max_batch: int = 64) -> List[List[int]]:
+        """Variable-length input: a list of 1-D PCM tensors -> token ids per utterance, in input order.
+        The reference's collator pads with zeros and never masks (data.py:145-203), which makes an
+        utterance's result depend on its batch mates; here utterances of equal length are batched
+        together (at most `max_batch` per launch sequence) and nothing is padded, so every result equals
+        transcribe() of that utterance alone."""
+        out: List[Optional[List[int]]] = [None] * len(utterances)
+        groups: Dict[int, List[int]] = {}
+        for i, u in enumerate(utterances):
+            if u.dim() != 1:
+                raise RuntimeError("transcribe_list takes 1-D PCM tensors")
+            groups.setdefault(int(u.numel()), []).append(i)
+        dev = self._device()
+        for _, idx in sorted(groups.items()):
+            for j in range(0, len(idx), max_batch):
+                part = idx[j:j + max_batch]
+                batch = torch.stack([utterances[i].to(dev, torch.float32) for i in part])
+                for i, toks in zip(part, self.transcribe(batch)):
+                    out[i] = toks
+        return out  # type: ignore[return-value]
+
     def extend_positional_table(self, rows: int) -> None:
         """Regenerate pe_time with `rows` rows by the formula of model.py:94-100.  The reference
         stops at 5000 tokens (~100 s) and raises beyond; long-form input needs a longer table."""
@@ -249,7 +271,16 @@ class VELOCITYASR(nn.Module):
             raise NotImplementedError(
                 "Model hub download not yet implemented. Please provide a local path to the checkpoint.")
         ckpt = torch.load(model_name_or_path, map_location="cpu")
-        cfg = VelocityASRConfig.from_dict(ckpt["config"]) if "config" in ckpt else VelocityASRConfig()
+        # save_pretrained files carry the model config under 'config' (model.py:455-460); Trainer
+        # checkpoints carry the TRAINING config there and the model's under 'model_config'
+        # (training.py:382-397) — the reference reads the wrong one and silently falls back to defaults
+        # (SURVEY.md 5.4); prefer 'model_config' when it is present.
+        if "model_config" in ckpt:
+            cfg = VelocityASRConfig.from_dict(dict(ckpt["model_config"]))
+        elif "config" in ckpt:
+            cfg = VelocityASRConfig.from_dict(dict(ckpt["config"]))
+        else:
+            cfg = VelocityASRConfig()
         model = cls(cfg)
         sd = ckpt["model_state_dict"] if "model_state_dict" in ckpt else ckpt
         rows = sd["temporal_binding.pos_encoding.pe_time"].shape[0]
