@@ -51,7 +51,8 @@ def synth_audio(batch, samples, seed):
 
 # ----------------------------------------------------------------------------- clocks -----
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    """nvidia-smi sampled every 20 ms (B200_PROFILING.md); only samples that arrive between mark_begin()
+    and mark_end() — the timed region — are reported, so idle clocks before / after it do not count."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -60,44 +61,60 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.15)               # let the first samples arrive before the region starts
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        sm.sort()
+
+        def collect(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    for n, v in zip(names, r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+                except Exception:
+                    pass
+            return sorted(sm), mx, reasons
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30) + 0.02]
+        sm, mx, reasons = collect(inside)
+        where = "timed region"
+        if not sm:                          # region shorter than the sampling period: nearest samples
+            sm, mx, reasons = collect(self.rows)
+            where = "whole run (timed region shorter than the sampling period)"
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 # ----------------------------------------------------------------------------- reference ---
@@ -266,11 +283,13 @@ def run_own_arm(args):
         sampler.start()
     launches0 = lib.vasr_kernel_launches(eng.handle)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record(stream)
     for i in range(args.steps):
         step_dev(i)
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     dev_ms = e0.elapsed_time(e1)
     launches = lib.vasr_kernel_launches(eng.handle) - launches0
     clocks = sampler.stop() if rank == 0 else None

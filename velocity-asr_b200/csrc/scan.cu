@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 :
       mufu_phase(cur, r, e, rq);
       pack_phase(cur, r, e, rq, pre);
     }
-#pragma unroll 1
+#pragma unroll 4   // the whole 16-step chunk: no loop-carried register copies, no issue bubble at block ends (0.315 -> 0.292 ms)
     for (int g4 = 0; g4 < TCH; g4 += 4) {
       if (g4 >= tcn) break;
       float yp[NV];   // index RPL*i + r : step i, row r
