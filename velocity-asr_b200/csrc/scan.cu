@@ -643,9 +643,12 @@ cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
       (reinterpret_cast<uintptr_t>(a.y) & 7))
     return cudaErrorInvalidValue;
   static const int rpl_env = [] { const char* e = getenv("VASR_SCAN_RPL"); return e ? atoi(e) : 0; }();
-  const int rpl = rpl_env == 1 || rpl_env == 2 ? rpl_env : 2;
+  const int rpl = rpl_env >= 1 && rpl_env <= 3 ? rpl_env : 2;
   static const int warps_env = [] { const char* e = getenv("VASR_SCAN_WARPS"); return e ? atoi(e) : 0; }();
-  if (rpl == 2) {
+  if constexpr (LPR == 4) {
+    if (rpl == 3 && a.Di % (4 * G * 3) == 0) return launch_seq<LPR, 4, 3>(a, s);
+  }
+  if (rpl >= 2) {
     // four warps = one warp of the CTA per SM sub-partition: the warps of a CTA then advance at the
     // same rate and the per-chunk barrier costs nothing (measured 0.320 ms vs 0.356 ms with three)
     if (LPR == 4 && warps_env != 3 && a.Di % (4 * G * 2) == 0) return launch_seq<LPR, 4, 2>(a, s);
