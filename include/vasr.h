@@ -161,9 +161,11 @@ int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float
  * The kernel reads the weight as two TF32 matrices [hi | lo] (2*N*K floats) made by
  * vasr_split_tf32; pass w_split_dev = NULL to have the call split w_dev on the fly. */
 int vasr_split_tf32(const float* w_dev, float* split_dev, int64_t numel, void* stream);
+/* resid_dev (M, N) with row stride ldr, or NULL: added after the activation (the residual adds of
+ * ssm.py:418-425 are fused this way). */
 int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* w_split_dev,
-                   const float* bias_dev, float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N,
-                   int act, void* stream);
+                   const float* bias_dev, const float* resid_dev, int64_t ldr, float* out_dev, int64_t ldo,
+                   int64_t M, int64_t K, int64_t N, int act, void* stream);
 
 /* ---- bookkeeping for the bench: kernels launched by this handle since creation, and the
  * share of the last vasr_transcribe spent in the scan (device ms, CUDA events on `stream`)

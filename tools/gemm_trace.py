@@ -14,12 +14,24 @@ M, K, N = [int(v) for v in sys.argv[1:4]] if len(sys.argv) > 3 else (48064, 192,
 x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
 ws = va.split_tf32(w)
 for _ in range(3): va.linear(x, w, None, tensor_cores=True, weight_split=ws)
-buf = torch.zeros(5 * 128, dtype=torch.int64, device="cuda")
+buf = torch.zeros(12 * 128 + 2 * 148, dtype=torch.int64, device="cuda")
 fn(ctypes.c_void_p(buf.data_ptr()))
 va.linear(x, w, None, tensor_cores=True, weight_split=ws)
 torch.cuda.synchronize()
 fn(None)
-t = buf.cpu().view(5, 128)
+cta = buf[12 * 128:].cpu().view(148, 2)
+t0 = int(cta[:, 0].min())
+dur = [(int(c[1]) - int(c[0])) / 1e3 for c in cta]
+start = [(int(c[0]) - t0) / 1e3 for c in cta]
+end = [(int(c[1]) - t0) / 1e3 for c in cta]
+print('per-CTA (us): start min/max %.1f/%.1f  duration min/med/max %.1f/%.1f/%.1f  last end %.1f' % (min(start), max(start), min(dur), sorted(dur)[74], max(dur), max(end)))
+print('durations of CTAs 0..15:', [round(d, 1) for d in dur[:16]])
+t = buf[:12 * 128].cpu().view(12, 128)
+print('epilogue warp 6: per tile  wait-for-accumulator (E1-E0)  own-work (E0[i+1]-E1[i])  | MMA: tile period')
+nk = (K + 31) // 32
+for i in range(8):
+    E0, E1, E0n = int(t[5, i]), int(t[6, i]), int(t[5, i + 1])
+    print(f'  tile {i}: wait {E1 - E0:6d}  work {E0n - E1:6d}  (chunk 0: tcgen05.ld {int(t[7, i]) - E1:5d}, to smem {int(t[8, i]) - int(t[7, i]):5d}, read-back+store {int(t[9, i]) - int(t[8, i]):5d})   mma issue span {int(t[4, (i + 1) * nk - 1]) - int(t[3, i * nk]):6d}')
 base = int(t[0, 0])
 print("stage   P(issue)  C0(full)  C1(conv)  M0(go)  M1(issued) | tma=C0-P conv=C1-C0 wake=M0-C1 issue=M1-M0 period=P[i]-P[i-1]")
 import statistics

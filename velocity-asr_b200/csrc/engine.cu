@@ -118,6 +118,10 @@ struct vasr_handle {
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
 
+  // VASR_PROF=1: CUDA-event pairs around every projection launch, aggregated by shape (tools/gemm_profile.py)
+  int prof = 0;
+  struct ProfEntry { std::string tag; cudaEvent_t e0, e1; };
+  std::vector<ProfEntry> prof_ev;
   // timing of the scan launches inside the last transcribe/forward
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // pairs
@@ -489,7 +493,22 @@ int calibrate_site(vasr_handle* h, const GemmArgs& g, const QSite& q, float* scr
   return VASR_OK;
 }
 
+int gemm_impl(vasr_handle* h, GemmArgs& g, cudaStream_t s);
 int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
+  if (!h->prof) return gemm_impl(h, g, s);
+  vasr_handle::ProfEntry pe;
+  pe.tag = "M" + std::to_string(g.M) + " K" + std::to_string(g.K) + " N" + std::to_string(g.N) + " act" +
+           std::to_string(g.act) + (g.resid ? " resid" : "") + (g.pe_time ? " pe" : "") + (g.q_scale ? " quant" : "");
+  CK(cudaEventCreate(&pe.e0));
+  CK(cudaEventCreate(&pe.e1));
+  CK(cudaEventRecord(pe.e0, s));
+  const int r = gemm_impl(h, g, s);
+  CK(cudaEventRecord(pe.e1, s));
+  h->prof_ev.push_back(pe);
+  return r;
+}
+
+int gemm_impl(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
   if (h->use_tc && (!g.blocked_sum || h->dft_tc)) {
     RET(split_of(h, g.W, g.N * g.K, s, &g.W_split));
     cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
@@ -766,6 +785,7 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   if (const char* ev = getenv("VASR_GEMM")) h->use_tc = strcmp(ev, "simt") != 0;
   if (const char* ev = getenv("VASR_DFT")) h->dft_tc = strcmp(ev, "tc") == 0;
   if (const char* ev = getenv("VASR_MEL")) h->mel_dft = strcmp(ev, "dft") == 0;
+  if (const char* ev = getenv("VASR_PROF")) h->prof = atoi(ev);
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -1144,8 +1164,8 @@ int vasr_split_tf32(const float* w_dev, float* split_dev, int64_t numel, void* s
 }
 
 int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const float* w_split_dev,
-                   const float* bias_dev, float* out_dev, int64_t ldo, int64_t M, int64_t K, int64_t N, int act,
-                   void* stream) {
+                   const float* bias_dev, const float* resid_dev, int64_t ldr, float* out_dev, int64_t ldo, int64_t M,
+                   int64_t K, int64_t N, int act, void* stream) {
   if (!x_dev || (!w_dev && !w_split_dev) || !out_dev) return fail(VASR_ERR_INVALID, "null argument");
   if (act < 0 || act > 3) return fail(VASR_ERR_INVALID, "unknown activation");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1155,6 +1175,7 @@ int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const fl
   GemmArgs g;
   g.A = x_dev; g.lda = ldx; g.W = w_dev; g.bias = bias_dev; g.C = out_dev; g.ldc = ldo;
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
+  g.resid = resid_dev; g.ldr = ldr;
   float* hl = nullptr;
   if (!w_split_dev) {       // split on the fly (one extra pass over the weights)
     CK(cudaMallocAsync(reinterpret_cast<void**>(&hl), (size_t)2 * N * K * sizeof(float), s));
@@ -1173,6 +1194,31 @@ int vasr_linear_tc(const float* x_dev, int64_t ldx, const float* w_dev, const fl
  * projection launches fills with clock64 at its pipeline events; NULL switches it off. */
 int vasr_debug_gemm_trace(long long* dev_buf) {
   g_trace = dev_buf;
+  return VASR_OK;
+}
+
+/* debug hook (not in vasr.h): prints and clears the per-shape projection timings gathered under VASR_PROF=1 */
+int vasr_debug_dump_profile(vasr_handle* h) {
+  if (!h) return fail(VASR_ERR_INVALID, "null handle");
+  CK(cudaDeviceSynchronize());
+  std::unordered_map<std::string, std::pair<int, float>> agg;
+  float total = 0.f;
+  for (auto& pe : h->prof_ev) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pe.e0, pe.e1);
+    auto& a = agg[pe.tag];
+    a.first += 1;
+    a.second += ms;
+    total += ms;
+    cudaEventDestroy(pe.e0);
+    cudaEventDestroy(pe.e1);
+  }
+  h->prof_ev.clear();
+  for (auto& kv : agg)
+    printf("%-44s x%3d  total %8.3f ms  avg %7.1f us\n", kv.first.c_str(), kv.second.first, kv.second.second,
+           1e3f * kv.second.second / kv.second.first);
+  printf("projections total %.3f ms\n", total);
+  fflush(stdout);
   return VASR_OK;
 }
 

@@ -153,6 +153,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -204,12 +216,17 @@ struct TcArgs {
 // count that divides the grid every tile of a CTA would have the same n index, and the CTAs that own
 // the narrow last n-tile would do half the work of the others.  The n index is therefore rotated by
 // the round number, so each CTA sees every n-tile in turn.
-__device__ __forceinline__ void tile_coords(const TcArgs& g, int64_t tile, int64_t units, int64_t* mt, int* nt) {
-  *mt = tile / g.n_tiles;
-  const int64_t per = units / g.n_tiles > 0 ? units / g.n_tiles : 1;
-  *nt = (int)((tile % g.n_tiles + (g.rotate_n ? *mt / per : 0)) % g.n_tiles);
+__device__ __forceinline__ void tile_coords(const TcArgs& g, int64_t tile64, int64_t units, int64_t* mt, int* nt) {
+  // 32-bit arithmetic: tile counts are checked to fit by the launcher, and a 64-bit division is a ~150-clock
+  // software routine that sat on the producer's and the MMA warp's per-tile path
+  const uint32_t tile = (uint32_t)tile64, n_tiles = (uint32_t)g.n_tiles;
+  const uint32_t m = tile / n_tiles;
+  const uint32_t per = (uint32_t)units / n_tiles > 0 ? (uint32_t)units / n_tiles : 1u;
+  *mt = m;
+  *nt = (int)((tile - m * n_tiles + (g.rotate_n ? m / per : 0u)) % n_tiles);
 }
 constexpr int TRACE_SLOTS = 128;
+constexpr int TRACE_ROLES = 12;
 __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
 }
@@ -257,6 +274,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
   const int64_t UNITS = gridDim.x;
+  if (g.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[TRACE_ROLES * TRACE_SLOTS + 2 * blockIdx.x] = (long long)t;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -267,8 +289,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int nt;
       int64_t mt;
       tile_coords(g, tile, UNITS, &mt, &nt);
-      const int batch = (int)(mt / g.m_tiles_per_batch);
-      const int mi0 = (int)(mt % g.m_tiles_per_batch) * TBM;
+      const int batch = (int)((uint32_t)mt / (uint32_t)g.m_tiles_per_batch);
+      const int mi0 = (int)((uint32_t)mt % (uint32_t)g.m_tiles_per_batch) * TBM;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
         if (lane == 0) trace_ev(g, 0, tr_i);
@@ -365,94 +387,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
-    // A warp reads a 32-row x 32-column chunk of the accumulator (thread = row), transposes it
-    // through its private 4 KB of shared memory (16-byte chunks XOR-swizzled by row: conflict-free
-    // both ways) and then owns 128-byte row segments: lane l handles columns 4*(l&7).. of rows
-    // (l>>3) + 4*i, so bias / activation / pos-enc / residual and the store are all coalesced.
+    // A warp reads two 32-row x 32-column chunks of the accumulator (thread = row), hands the accumulator
+    // back as soon as both are in registers, transposes each chunk through its private 4 KB of shared
+    // memory (16-byte chunks XOR-swizzled by row: conflict-free both ways) and then owns 128-byte row
+    // segments: lane l handles columns 4*(l&7).. of rows (l>>3) + 4*i, so bias / activation / pos-enc /
+    // residual and the store are coalesced.  Everything that does not depend on the accumulator (tile
+    // coordinates in 32-bit arithmetic, bias, the residual rows of the first chunk) is fetched BEFORE the
+    // wait for the accumulator: a trace showed 5.2 k clocks of epilogue per tile against 5.4 k of MMA.
     const int q = warp & 3;                         // TMEM lane quadrant this warp may read
     const int chalf = (warp - 6) >> 2;              // which two of the four 32-column chunks
     uint8_t* stg = smem + STAGES * STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES;
     const int cc = lane & 7, rsub = lane >> 3;
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int nt;
-      int64_t mt;
-      tile_coords(g, tile, UNITS, &mt, &nt);
-      const int64_t batch = mt / g.m_tiles_per_batch;
-      const int64_t mi0 = (mt % g.m_tiles_per_batch) * TBM + q * 32;    // first row (within the batch) of this warp
-      const int64_t ncol0 = (int64_t)nt * TBN;
-      const int64_t nrem = g.N - ncol0;
-      const int nchunks = nrem >= TBN ? 4 : (int)((nrem + 31) >> 5);    // 32-column chunks that hold real columns
-      const uint32_t acc = (uint32_t)(it & 1);
-      mbar_wait(BAR(B_TFULL + acc), (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
+    const uint32_t n_tiles = (uint32_t)g.n_tiles, mtpb = (uint32_t)g.m_tiles_per_batch;
+    const uint32_t per = (uint32_t)UNITS / n_tiles > 0 ? (uint32_t)UNITS / n_tiles : 1u;
+    const uint32_t rpb = (uint32_t)g.rows_per_batch;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < (uint32_t)total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t mt = tile / n_tiles;
+      const uint32_t nt = (tile % n_tiles + (g.rotate_n ? mt / per : 0u)) % n_tiles;
+      const uint32_t batch = mt / mtpb;
+      const uint32_t mi0 = (mt % mtpb) * TBM + q * 32;                 // first row (within the batch) of this warp
+      const uint32_t ncol0 = nt * TBN;
+      const uint32_t nrem = (uint32_t)g.N - ncol0;
+      const int nchunks = nrem >= (uint32_t)TBN ? 4 : (int)((nrem + 31) >> 5);   // chunks that hold real columns
+      const uint32_t acc = it & 1u;
       const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
+      // this lane's four columns in chunk c_begin (+32 for the second chunk), and its row pointers
+      const uint32_t n0 = ncol0 + c_begin * 32 + 4 * cc;
+      const int64_t mrow0 = (int64_t)batch * rpb + mi0;               // global row of the warp's first row
+      float* crow = g.C + mrow0 * g.ldc + n0;
+      const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
+      float4 b4[2], qs4[2], qz4[2], pf4[2];
+      bool col_ok[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t n = n0 + 32 * j;
+        col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;       // N % 4 == 0: the group is valid as a whole
+        b4[j] = qs4[j] = qz4[j] = pf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        if (QUANT && col_ok[j]) {
+          qs4[j] = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
+          qz4[j] = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
+        }
+        if (PE && col_ok[j] && n >= (uint32_t)g.pe_half)
+          pf4[j] = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
+      }
+      float4 r4[8];
+      auto load_resid = [&](int j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = 4 * i + rsub;
+          r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (RESID && col_ok[j] && mi0 + rr < rpb)
+            r4[i] = __ldg(reinterpret_cast<const float4*>(rrow + (int64_t)rr * g.ldr + 32 * j));
+        }
+      };
+      if (RESID) load_resid(0);
+      if (threadIdx.x == 192) trace_ev(g, 5, (int)it);     // ready to take tile `it`
+      mbar_wait(BAR(B_TFULL + acc), (it >> 1) & 1u);
+      if (threadIdx.x == 192) trace_ev(g, 6, (int)it);     // accumulator complete
+      tc_fence_after();
       if (c_begin >= c_end) {       // nothing of this tile belongs to this warp: hand the accumulator back
         tc_fence_before();
         mbar_arrive(BAR(B_TEMPTY + acc));
         continue;
       }
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
-        if (c == c_end - 1) {       // this warp's share of the accumulator is in registers
-          tc_fence_before();
-          mbar_arrive(BAR(B_TEMPTY + acc));
-        }
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
+      tmem_ld32_issue(taddr, v0);
+      if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + acc));   // this warp's share of the accumulator is in registers
+      if (threadIdx.x == 192) trace_ev(g, 7, (int)it);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (c_begin + j >= c_end) break;
         {
           uint8_t* srow = stg + lane * 128;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
-                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                j == 0 ? make_uint4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3])
+                       : make_uint4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]);
         }
         __syncwarp();
-        const int64_t n = ncol0 + c * 32 + 4 * cc;      // this lane's four columns
-        const bool col_ok = n < g.N;                     // N % 4 == 0: the group is valid or not as a whole
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
-        if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-        float4 qs4 = make_float4(0.f, 0.f, 0.f, 0.f), qz4 = qs4;
-        if (QUANT && col_ok) {
-          qs4 = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
-          qz4 = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
-        }
-        if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
-        const bool act_on = ACT != ACT_NONE && n >= g.act_from;
+        if (threadIdx.x == 192 && j == 0) trace_ev(g, 8, (int)it);
+        const uint32_t n = n0 + 32 * j;
+        const bool act_on = ACT != ACT_NONE && n >= (uint32_t)g.act_from;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + rsub;
-          const int64_t mi = mi0 + rr;
+          const uint32_t rr = 4 * i + rsub;
           float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          if (!col_ok || mi >= g.rows_per_batch) continue;
-          const int64_t m = batch * g.rows_per_batch + mi;
-          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
           if (QUANT) {
-            x.x = fake_quant_u8(x.x, qs4.x, qz4.x); x.y = fake_quant_u8(x.y, qs4.y, qz4.y);
-            x.z = fake_quant_u8(x.z, qs4.z, qz4.z); x.w = fake_quant_u8(x.w, qs4.w, qz4.w);
+            x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
+            x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
           }
           if (act_on) {
             x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
             x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
           }
           if (PE) {
-            float4 p4 = pf4;
-            if (n < g.pe_half) p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + mi * g.pe_half + n));
+            float4 p4 = pf4[j];
+            if (n < (uint32_t)g.pe_half && col_ok[j] && mi0 + rr < rpb)
+              p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + (int64_t)(mi0 + rr) * g.pe_half + n));
             x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
           }
-          if (RESID) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(g.resid + m * g.ldr + n));
-            x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-          }
-          *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = x;
+          if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
+          if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
         }
-        __syncwarp();               // the staging chunk is rewritten by the next iteration
+        __syncwarp();               // the staging chunk is rewritten by the next chunk
+        if (RESID && j == 0 && c_begin + 1 < c_end) load_resid(1);
+        if (threadIdx.x == 192 && j == 0) trace_ev(g, 9, (int)it);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (g.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[TRACE_ROLES * TRACE_SLOTS + 2 * blockIdx.x + 1] = (long long)t;
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -596,8 +654,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int nt;
       int64_t mt;
       tile_coords(g, tile, UNITS, &mt, &nt);
-      const int batch = (int)(mt / g.m_tiles_per_batch);
-      const int mi0 = (int)(mt % g.m_tiles_per_batch) * 2 * TBM + (int)rank * TBM;
+      const int batch = (int)((uint32_t)mt / (uint32_t)g.m_tiles_per_batch);
+      const int mi0 = (int)((uint32_t)mt % (uint32_t)g.m_tiles_per_batch) * 2 * TBM + (int)rank * TBM;
       int64_t nrem = g.N - (int64_t)nt * TBN;
       const int n_mma = nrem >= TBN ? TBN : (int)((nrem + 15) & ~15LL);
       const int wrow = nt * TBN + (int)rank * (n_mma / 2);       // this CTA's half of the W rows of the tile
@@ -902,6 +960,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.rotate_n = rot_env;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
+  if (tiles >= (1LL << 31) || rpb >= (1LL << 31)) return cudaErrorNotSupported;
   const int64_t units = pair ? num_sms / 2 : num_sms;
   const unsigned grid = (unsigned)((tiles < units ? tiles : units) * (pair ? 2 : 1));
   const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;

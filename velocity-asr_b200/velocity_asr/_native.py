@@ -47,8 +47,8 @@ _SIGNATURES = {
     "vasr_get_quant_params": (c_int, [c_void_p, c_char_p, POINTER(c_float), POINTER(c_float)]),
     "vasr_set_quant_params": (c_int, [c_void_p, c_char_p, c_float, c_float]),
     "vasr_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                               c_int64, c_int, c_void_p]),
+    "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                               c_int64, c_int64, c_int64, c_int, c_void_p]),
     "vasr_kernel_launches": (c_int64, [c_void_p]),
     "vasr_tc_launches": (c_int64, [c_void_p]),
     "vasr_workspace_bytes": (c_int64, [c_void_p]),

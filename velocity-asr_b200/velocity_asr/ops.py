@@ -75,24 +75,31 @@ def split_tf32(weight: torch.Tensor) -> torch.Tensor:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            activation: Optional[str] = None, tensor_cores: bool = False,
-           weight_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+           weight_split: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.linear (+ optional activation) on (..., K) rows.  tensor_cores=False: CUDA-core fp32 kernel
     (K % 16 == 0); True: tcgen05 3xTF32 kernel (K % 4 == 0, N % 4 == 0) — the one the model's
-    token-sized projections run on; weight_split = split_tf32(weight) skips the per-call split."""
+    token-sized projections run on; weight_split = split_tf32(weight) skips the per-call split; residual
+    (same shape as the result, tensor_cores only) is added after the activation; out = preallocated result."""
     if x.device.type != "cuda":
         raise RuntimeError("linear runs on CUDA only (no CPU fallback)")
     x, weight, bias = map(_f32c, (x, weight, bias))
     K = x.shape[-1]
     N = weight.shape[0]
     x2 = x.reshape(-1, K)
-    out = torch.empty(x2.shape[0], N, device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(x2.shape[0], N, device=x.device, dtype=torch.float32)
+    if residual is not None:
+        if not tensor_cores:
+            raise NotImplementedError("residual is fused in the tensor-core kernel only")
+        residual = _f32c(residual).reshape(-1, N)
     if x2.shape[0] > 0:
         lib = _native.lib()
         with torch.cuda.device(x.device):
             if tensor_cores:
                 _native.check(lib.vasr_linear_tc(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(weight_split),
-                                                 _native.ptr(bias), _native.ptr(out), N, x2.shape[0], K, N,
-                                                 _ACT[activation], _stream(x.device)))
+                                                 _native.ptr(bias), _native.ptr(residual), N, _native.ptr(out), N,
+                                                 x2.shape[0], K, N, _ACT[activation], _stream(x.device)))
             else:
                 _native.check(lib.vasr_linear(_native.ptr(x2), K, _native.ptr(weight), _native.ptr(bias),
                                               _native.ptr(out), N, x2.shape[0], K, N, _ACT[activation],
