@@ -105,6 +105,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tile of the 3-D map: the persistent CTA knows its next tile a whole tile ahead, and an A tile
+// that still sits in HBM costs a TMA load 2-3 k clocks — more than four 900-clock stages can hide
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -209,6 +215,8 @@ struct TcArgs {
   const float* pe_time;
   const float* pe_freq;
   int pe_half;
+  int prefetch;       // producer prefetches the next tile's A k-blocks into L2
+  int dbg;            // debug (VASR_TC_DBG): 1 = epilogue skips its TMEM loads, 2 = skips staging + stores (garbage output)
   int rotate_n;       // rotate the n-tile index by the round number (see tile_coords)
   long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
 };
@@ -291,6 +299,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(g, tile, UNITS, &mt, &nt);
       const int batch = (int)((uint32_t)mt / (uint32_t)g.m_tiles_per_batch);
       const int mi0 = (int)((uint32_t)mt % (uint32_t)g.m_tiles_per_batch) * TBM;
+      if (g.prefetch && tile + gridDim.x < total_tiles) {
+        int nnt;
+        int64_t nmt;
+        tile_coords(g, tile + gridDim.x, UNITS, &nmt, &nnt);
+        const int nbatch = (int)((uint32_t)nmt / (uint32_t)g.m_tiles_per_batch);
+        const int nmi0 = (int)((uint32_t)nmt % (uint32_t)g.m_tiles_per_batch) * TBM;
+        if (elect_one())
+          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_3d(&tmA, kb * TBK, nmi0, nbatch);
+        __syncwarp();
+      }
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
         if (lane == 0) trace_ev(g, 0, tr_i);
@@ -454,12 +472,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
-      tmem_ld32_issue(taddr, v0);
-      if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
-      tmem_ld_wait();
+      if (!(g.dbg & 1)) {
+        tmem_ld32_issue(taddr, v0);
+        if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v0[k] = v1[k] = 0u;
+      }
       tc_fence_before();
       mbar_arrive(BAR(B_TEMPTY + acc));   // this warp's share of the accumulator is in registers
       if (threadIdx.x == 192) trace_ev(g, 7, (int)it);
+      if (g.dbg & 2) continue;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (c_begin + j >= c_end) break;
@@ -958,6 +982,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.trace = g_trace;
   static const int rot_env = [] { const char* e = getenv("VASR_TC_ROT"); return e ? atoi(e) : 1; }();
   a.rotate_n = rot_env;
+  static const int dbg_env = [] { const char* e = getenv("VASR_TC_DBG"); return e ? atoi(e) : 0; }();
+  a.dbg = dbg_env;
+  static const int pf_env = [] { const char* e = getenv("VASR_TC_PREFETCH"); return e ? atoi(e) : 0; }();   // measured: no gain
+  a.prefetch = pf_env;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
   if (tiles >= (1LL << 31) || rpb >= (1LL << 31)) return cudaErrorNotSupported;
