@@ -239,6 +239,150 @@ __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
 }
 
+// Epilogue of one warp over its tiles (shared by the single-CTA and the CTA-pair kernels).  PAIR: tiles are 256
+// rows shared by the two CTAs of a cluster (this CTA owns rows rank*128 ..), tile index strides over pairs, and
+// the accumulator-empty barrier lives in the leader CTA (arrive through its shared::cluster address).
+template <int ACT, bool PE, bool RESID, bool QUANT, bool PAIR>
+__device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
+                                              uint32_t tile_stride, uint32_t total_tiles32, uint32_t units, uint32_t rank,
+                                              uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
+  constexpr uint32_t tmem_base = 0u;
+  constexpr uint32_t TM = PAIR ? 2 * TBM : TBM;          // rows of one tile
+  auto BARF = [&](uint32_t acc) { return bar_tfull0 + 8u * acc; };
+  auto arrive_empty = [&](uint32_t acc) {
+    if (PAIR) {
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t r;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar_tempty0_local + 8u * acc), "r"(0u));
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+      }
+    } else {
+      mbar_arrive(bar_tempty0_local + 8u * acc);
+    }
+  };
+  // A warp reads two 32-row x 32-column chunks of the accumulator (thread = row), hands the accumulator
+  // back as soon as both are in registers, transposes each chunk through its private 4 KB of shared
+  // memory (16-byte chunks XOR-swizzled by row: conflict-free both ways) and then owns 128-byte row
+  // segments: lane l handles columns 4*(l&7).. of rows (l>>3) + 4*i, so bias / activation / pos-enc /
+  // residual and the store are coalesced.  Everything that does not depend on the accumulator (tile
+  // coordinates in 32-bit arithmetic, bias, the residual rows of the first chunk) is fetched BEFORE the
+  // wait for the accumulator: a trace showed 5.2 k clocks of epilogue per tile against 5.4 k of MMA.
+  const int q = warp & 3;                         // TMEM lane quadrant this warp may read
+  const int chalf = (warp - 6) >> 2;              // which two of the four 32-column chunks
+    const int cc = lane & 7, rsub = lane >> 3;
+  const uint32_t n_tiles = (uint32_t)g.n_tiles, mtpb = (uint32_t)g.m_tiles_per_batch;
+  const uint32_t per = units / n_tiles > 0 ? units / n_tiles : 1u;
+  const uint32_t rpb = (uint32_t)g.rows_per_batch;
+  uint32_t it = 0;
+  for (uint32_t tile = first_tile; tile < total_tiles32; tile += tile_stride, ++it) {
+    const uint32_t mt = tile / n_tiles;
+    const uint32_t nt = (tile % n_tiles + (g.rotate_n ? mt / per : 0u)) % n_tiles;
+    const uint32_t batch = mt / mtpb;
+    const uint32_t mi0 = (mt % mtpb) * TM + rank * TBM + q * 32;     // first row (within the batch) of this warp
+    const uint32_t ncol0 = nt * TBN;
+    const uint32_t nrem = (uint32_t)g.N - ncol0;
+    const int nchunks = nrem >= (uint32_t)TBN ? 4 : (int)((nrem + 31) >> 5);   // chunks that hold real columns
+    const uint32_t acc = it & 1u;
+    const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
+    // this lane's four columns in chunk c_begin (+32 for the second chunk), and its row pointers
+    const uint32_t n0 = ncol0 + c_begin * 32 + 4 * cc;
+    const int64_t mrow0 = (int64_t)batch * rpb + mi0;               // global row of the warp's first row
+    float* crow = g.C + mrow0 * g.ldc + n0;
+    const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
+    float4 b4[2], qs4[2], qz4[2], pf4[2];
+    bool col_ok[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t n = n0 + 32 * j;
+      col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;       // N % 4 == 0: the group is valid as a whole
+      b4[j] = qs4[j] = qz4[j] = pf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if (QUANT && col_ok[j]) {
+        qs4[j] = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
+        qz4[j] = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
+      }
+      if (PE && col_ok[j] && n >= (uint32_t)g.pe_half)
+        pf4[j] = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
+    }
+    float4 r4[8];
+    auto load_resid = [&](int j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = 4 * i + rsub;
+        r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RESID && col_ok[j] && mi0 + rr < rpb)
+          r4[i] = __ldg(reinterpret_cast<const float4*>(rrow + (int64_t)rr * g.ldr + 32 * j));
+      }
+    };
+    if (RESID) load_resid(0);
+    if (threadIdx.x == 192) trace_ev(g, 5, (int)it);     // ready to take tile `it`
+    mbar_wait(BARF(acc), (it >> 1) & 1u);
+    if (threadIdx.x == 192) trace_ev(g, 6, (int)it);     // accumulator complete
+    tc_fence_after();
+    if (c_begin >= c_end) {       // nothing of this tile belongs to this warp: hand the accumulator back
+      tc_fence_before();
+      arrive_empty(acc);
+      continue;
+    }
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
+    if (!(g.dbg & 1)) {
+      tmem_ld32_issue(taddr, v0);
+      if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v0[k] = v1[k] = 0u;
+    }
+    tc_fence_before();
+    arrive_empty(acc);                  // this warp's share of the accumulator is in registers
+    if (threadIdx.x == 192) trace_ev(g, 7, (int)it);
+    if (g.dbg & 2) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (c_begin + j >= c_end) break;
+      {
+        uint8_t* srow = stg + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
+              j == 0 ? make_uint4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3])
+                     : make_uint4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]);
+      }
+      __syncwarp();
+      if (threadIdx.x == 192 && j == 0) trace_ev(g, 8, (int)it);
+      const uint32_t n = n0 + 32 * j;
+      const bool act_on = ACT != ACT_NONE && n >= (uint32_t)g.act_from;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = 4 * i + rsub;
+        float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        if (QUANT) {
+          x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
+          x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
+        }
+        if (act_on) {
+          x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
+          x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+        }
+        if (PE) {
+          float4 p4 = pf4[j];
+          if (n < (uint32_t)g.pe_half && col_ok[j] && mi0 + rr < rpb)
+            p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + (int64_t)(mi0 + rr) * g.pe_half + n));
+          x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
+        }
+        if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
+        if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
+      }
+      __syncwarp();               // the staging chunk is rewritten by the next chunk
+      if (RESID && j == 0 && c_begin + 1 < c_end) load_resid(1);
+      if (threadIdx.x == 192 && j == 0) trace_ev(g, 9, (int)it);
+    }
+  }
+}
+
 template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
@@ -405,127 +549,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue =====================
-    // A warp reads two 32-row x 32-column chunks of the accumulator (thread = row), hands the accumulator
-    // back as soon as both are in registers, transposes each chunk through its private 4 KB of shared
-    // memory (16-byte chunks XOR-swizzled by row: conflict-free both ways) and then owns 128-byte row
-    // segments: lane l handles columns 4*(l&7).. of rows (l>>3) + 4*i, so bias / activation / pos-enc /
-    // residual and the store are coalesced.  Everything that does not depend on the accumulator (tile
-    // coordinates in 32-bit arithmetic, bias, the residual rows of the first chunk) is fetched BEFORE the
-    // wait for the accumulator: a trace showed 5.2 k clocks of epilogue per tile against 5.4 k of MMA.
-    const int q = warp & 3;                         // TMEM lane quadrant this warp may read
-    const int chalf = (warp - 6) >> 2;              // which two of the four 32-column chunks
-    uint8_t* stg = smem + STAGES * STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES;
-    const int cc = lane & 7, rsub = lane >> 3;
-    const uint32_t n_tiles = (uint32_t)g.n_tiles, mtpb = (uint32_t)g.m_tiles_per_batch;
-    const uint32_t per = (uint32_t)UNITS / n_tiles > 0 ? (uint32_t)UNITS / n_tiles : 1u;
-    const uint32_t rpb = (uint32_t)g.rows_per_batch;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < (uint32_t)total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t mt = tile / n_tiles;
-      const uint32_t nt = (tile % n_tiles + (g.rotate_n ? mt / per : 0u)) % n_tiles;
-      const uint32_t batch = mt / mtpb;
-      const uint32_t mi0 = (mt % mtpb) * TBM + q * 32;                 // first row (within the batch) of this warp
-      const uint32_t ncol0 = nt * TBN;
-      const uint32_t nrem = (uint32_t)g.N - ncol0;
-      const int nchunks = nrem >= (uint32_t)TBN ? 4 : (int)((nrem + 31) >> 5);   // chunks that hold real columns
-      const uint32_t acc = it & 1u;
-      const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
-      // this lane's four columns in chunk c_begin (+32 for the second chunk), and its row pointers
-      const uint32_t n0 = ncol0 + c_begin * 32 + 4 * cc;
-      const int64_t mrow0 = (int64_t)batch * rpb + mi0;               // global row of the warp's first row
-      float* crow = g.C + mrow0 * g.ldc + n0;
-      const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
-      float4 b4[2], qs4[2], qz4[2], pf4[2];
-      bool col_ok[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t n = n0 + 32 * j;
-        col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;       // N % 4 == 0: the group is valid as a whole
-        b4[j] = qs4[j] = qz4[j] = pf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-        if (QUANT && col_ok[j]) {
-          qs4[j] = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
-          qz4[j] = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
-        }
-        if (PE && col_ok[j] && n >= (uint32_t)g.pe_half)
-          pf4[j] = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
-      }
-      float4 r4[8];
-      auto load_resid = [&](int j) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t rr = 4 * i + rsub;
-          r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (RESID && col_ok[j] && mi0 + rr < rpb)
-            r4[i] = __ldg(reinterpret_cast<const float4*>(rrow + (int64_t)rr * g.ldr + 32 * j));
-        }
-      };
-      if (RESID) load_resid(0);
-      if (threadIdx.x == 192) trace_ev(g, 5, (int)it);     // ready to take tile `it`
-      mbar_wait(BAR(B_TFULL + acc), (it >> 1) & 1u);
-      if (threadIdx.x == 192) trace_ev(g, 6, (int)it);     // accumulator complete
-      tc_fence_after();
-      if (c_begin >= c_end) {       // nothing of this tile belongs to this warp: hand the accumulator back
-        tc_fence_before();
-        mbar_arrive(BAR(B_TEMPTY + acc));
-        continue;
-      }
-      uint32_t v0[32], v1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
-      if (!(g.dbg & 1)) {
-        tmem_ld32_issue(taddr, v0);
-        if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v0[k] = v1[k] = 0u;
-      }
-      tc_fence_before();
-      mbar_arrive(BAR(B_TEMPTY + acc));   // this warp's share of the accumulator is in registers
-      if (threadIdx.x == 192) trace_ev(g, 7, (int)it);
-      if (g.dbg & 2) continue;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (c_begin + j >= c_end) break;
-        {
-          uint8_t* srow = stg + lane * 128;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
-                j == 0 ? make_uint4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3])
-                       : make_uint4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]);
-        }
-        __syncwarp();
-        if (threadIdx.x == 192 && j == 0) trace_ev(g, 8, (int)it);
-        const uint32_t n = n0 + 32 * j;
-        const bool act_on = ACT != ACT_NONE && n >= (uint32_t)g.act_from;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t rr = 4 * i + rsub;
-          float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
-          if (QUANT) {
-            x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
-            x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
-          }
-          if (act_on) {
-            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
-            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
-          }
-          if (PE) {
-            float4 p4 = pf4[j];
-            if (n < (uint32_t)g.pe_half && col_ok[j] && mi0 + rr < rpb)
-              p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + (int64_t)(mi0 + rr) * g.pe_half + n));
-            x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
-          }
-          if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
-          if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
-        }
-        __syncwarp();               // the staging chunk is rewritten by the next chunk
-        if (RESID && j == 0 && c_begin + 1 < c_end) load_resid(1);
-        if (threadIdx.x == 192 && j == 0) trace_ev(g, 9, (int)it);
-      }
-    }
+    epilogue_loop<ACT, PE, RESID, QUANT, false>(g, smem + STAGES * STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+                                                blockIdx.x, gridDim.x, (uint32_t)total_tiles, (uint32_t)UNITS, 0u,
+                                                BAR(B_TFULL), BAR(B_TEMPTY));
   }
 
   tc_fence_before();
@@ -577,13 +603,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
       : "r"(bar), "r"(parity)
@@ -779,89 +805,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
-    const int q = warp & 3;
-    const int chalf = (warp - 6) >> 2;
-    uint8_t* stg = smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES;
-    const int cc = lane & 7, rsub = lane >> 3;
-    int64_t it = 0;
-    for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
-      int nt;
-      int64_t mt;
-      tile_coords(g, tile, UNITS, &mt, &nt);
-      const int64_t batch = mt / g.m_tiles_per_batch;
-      const int64_t mi0 = (mt % g.m_tiles_per_batch) * 2 * TBM + (int64_t)rank * TBM + q * 32;
-      const int64_t ncol0 = (int64_t)nt * TBN;
-      const int64_t nrem = g.N - ncol0;
-      const int nchunks = nrem >= TBN ? 4 : (int)((nrem + 31) >> 5);
-      const uint32_t acc = (uint32_t)(it & 1);
-      const uint32_t tempty = mapa(BAR(PB_TEMPTY + acc), 0);
-      mbar_wait_cluster(BAR(PB_TFULL + acc), (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      const int c_begin = 2 * chalf, c_end = (2 * chalf + 2 < nchunks) ? 2 * chalf + 2 : nchunks;
-      if (c_begin >= c_end) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty);
-        continue;
-      }
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c * 32, v);
-        if (c == c_end - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty);
-        }
-        {
-          uint8_t* srow = stg + lane * 128;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) =
-                make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        }
-        __syncwarp();
-        const int64_t n = ncol0 + c * 32 + 4 * cc;
-        const bool col_ok = n < g.N;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), pf4 = b4;
-        if (col_ok && g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-        float4 qs4 = make_float4(0.f, 0.f, 0.f, 0.f), qz4 = qs4;
-        if (QUANT && col_ok) {
-          qs4 = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
-          qz4 = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
-        }
-        if (PE && col_ok && n >= g.pe_half) pf4 = __ldg(reinterpret_cast<const float4*>(g.pe_freq + (n - g.pe_half)));
-        const bool act_on = ACT != ACT_NONE && n >= g.act_from;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + rsub;
-          const int64_t mi = mi0 + rr;
-          float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          if (!col_ok || mi >= g.rows_per_batch) continue;
-          const int64_t m = batch * g.rows_per_batch + mi;
-          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-          if (QUANT) {
-            x.x = fake_quant_u8(x.x, qs4.x, qz4.x); x.y = fake_quant_u8(x.y, qs4.y, qz4.y);
-            x.z = fake_quant_u8(x.z, qs4.z, qz4.z); x.w = fake_quant_u8(x.w, qs4.w, qz4.w);
-          }
-          if (act_on) {
-            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
-            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
-          }
-          if (PE) {
-            float4 p4 = pf4;
-            if (n < g.pe_half) p4 = __ldg(reinterpret_cast<const float4*>(g.pe_time + mi * g.pe_half + n));
-            x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
-          }
-          if (RESID) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(g.resid + m * g.ldr + n));
-            x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
-          }
-          *reinterpret_cast<float4*>(g.C + m * g.ldc + n) = x;
-        }
-        __syncwarp();
-      }
-    }
+    epilogue_loop<ACT, PE, RESID, QUANT, true>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+                                               (uint32_t)pair, (uint32_t)npairs, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
+                                               BAR(PB_TFULL), BAR(PB_TEMPTY));
   }
 
   tc_fence_before();
@@ -951,9 +897,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   if (g.pe_time && g.pe_rows != rpb) return cudaErrorNotSupported;   // pos-enc row == row within the batch
   const int64_t bstride = g.rows_per_batch > 0 ? g.batch_stride : rpb * g.lda;
 
-  // the CTA-pair kernel is correct but currently slower than the single-CTA one (its converter -> leader
-  // signalling is a cluster-scope arrive per warp per k-step): opt-in with VASR_GEMM=tc2
-  static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return e && strcmp(e, "tc2") == 0; }();
+  // CTA-pair kernel by default (4-7 % faster than the single-CTA one at config 2 once its cross-CTA barriers
+  // stopped using cluster-scope acquire / release, which ptxas turns into CCTL.IVALL + MEMBAR.GPU);
+  // VASR_GEMM=tc1 selects the single-CTA kernel
+  static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return !(e && strcmp(e, "tc1") == 0); }();
   const bool pair = use_pair && num_sms >= 2;
   CUtensorMap tmA, tmWh, tmWl;
   {

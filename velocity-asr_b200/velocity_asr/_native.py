@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvasr.so")
+LIB_PATH = os.environ.get("VASR_LIB") or os.path.join(_HERE, "libvasr.so")   # VASR_LIB: A/B runs of two builds
 
 OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = range(6)
 SCAN_MODE_ID = {"sequential": 0, "parallel": 1, "mamba": 2}
