@@ -579,13 +579,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // multicast to both CTAs by tcgen05.commit.
 // =============================================================================================
 constexpr int P_STAGE_BYTES = 2 * TILE_BYTES;                         // A (16 KB) | W_hi half (8 KB) | W_lo half (8 KB)
-constexpr int P_STAGES = 4;
+constexpr int P_STAGES = 6;                                          // shared-memory stages (32 KB each)
+constexpr int P_ASLOTS = 4;                                          // A (hi | lo) slots in TMEM, 64 columns each
 constexpr int P_BAR_OFFSET = P_STAGES * P_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
-constexpr int P_SMEM_BYTES = P_BAR_OFFSET + 256 + 1024;
+constexpr int P_SMEM_BYTES = P_BAR_OFFSET + 512 + 1024;
+static_assert(P_SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 // barrier indices (per CTA; the leader's copies of WFULL / CONV / TEMPTY are the ones in use)
 constexpr int PB_AFULL = 0, PB_WFULL = P_STAGES, PB_CONV = 2 * P_STAGES, PB_EMPTY = 3 * P_STAGES,
-              PB_TFULL = 4 * P_STAGES, PB_TEMPTY = 4 * P_STAGES + 2;
-constexpr int P_NBARS = 4 * P_STAGES + 4;
+              PB_TFULL = 4 * P_STAGES, PB_TEMPTY = 4 * P_STAGES + 2, PB_AFREE = 4 * P_STAGES + 4;
+constexpr int P_NBARS = 4 * P_STAGES + 4 + P_ASLOTS;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -675,6 +677,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(BAR(PB_TFULL + a), 1);                    // local, multicast tcgen05.commit
       mbar_init(BAR(PB_TEMPTY + a), 2 * EPI_WARPS);       // leader: one arrive per epilogue warp of both CTAs
     }
+    for (int a = 0; a < P_ASLOTS; ++a) mbar_init(BAR(PB_AFREE + a), 1);   // local, multicast tcgen05.commit
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -729,7 +732,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, cnt = 0;     // cnt: k-steps issued so far (TMEM A slot = cnt % P_ASLOTS)
       int64_t it = 0;
       int tr_i = 0;
       for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
@@ -751,7 +754,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) trace_ev(g, 3, tr_i);
           const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
           const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + TILE_BYTES + TILE_BYTES / 2);
-          const uint32_t a_hi = tmem_base + TMEM_A0 + stage * 64, a_lo = a_hi + 32;
+          const uint32_t slot = cnt % P_ASLOTS;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + slot * 64, a_lo = a_hi + 32;
           if (elect_one()) {
 #pragma unroll
             for (int k4 = 0; k4 < TBK / 8; ++k4) {
@@ -761,10 +765,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               umma_tf32_ts_pair(tmem_d, a_hi + 8 * k4, db_hi + adv, idesc, 1);
             }
             umma_commit_pair(BAR(PB_EMPTY + stage));
+            umma_commit_pair(BAR(PB_AFREE + slot));
             if (kb == nkb - 1) umma_commit_pair(BAR(PB_TFULL + acc));
             trace_ev(g, 4, tr_i);
           }
           ++tr_i;
+          ++cnt;
           __syncwarp();
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -775,7 +781,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, cnt = 0;
     int tr_i = 0;
     for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
       for (int kb = 0; kb < nkb; ++kb) {
@@ -791,15 +797,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           hi[4 * c + 2] = rna_tf32(v.z); lo[4 * c + 2] = rna_tf32(v.z - __uint_as_float(hi[4 * c + 2]));
           hi[4 * c + 3] = rna_tf32(v.w); lo[4 * c + 3] = rna_tf32(v.w - __uint_as_float(hi[4 * c + 3]));
         }
+        // the TMEM slot is free once the MMAs of its previous use (P_ASLOTS k-steps ago) have completed
+        const uint32_t slot = cnt % P_ASLOTS;
+        mbar_wait(BAR(PB_AFREE + slot), ((cnt / P_ASLOTS) & 1u) ^ 1u);
         tc_fence_after();
-        tmem_st32(lane_addr + stage * 64, hi);
-        tmem_st32(lane_addr + stage * 64 + 32, lo);
+        tmem_st32(lane_addr + slot * 64, hi);
+        tmem_st32(lane_addr + slot * 64 + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa(BAR(PB_CONV + stage), 0));
         if (threadIdx.x == 64) trace_ev(g, 2, tr_i);
         ++tr_i;
+        ++cnt;
         if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
       }
     }
