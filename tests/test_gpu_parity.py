@@ -156,6 +156,29 @@ def test_scan_oracle(va, n, structured, mode):
     assert rel(y0, O.selective_scan(d(x), d(dt), d(A), d(Bm), d(Cm), None, mode)) < 1e-4
 
 
+def test_scan_scaled_state_extremes(va):
+    """The structured-A kernel carries the state divided by u = x*dt (scan.cu): exact zeros, denormal-sized and
+    huge inputs, sign flips and long zero runs must not disturb it."""
+    rs = np.random.RandomState(12)
+    B, L, Di, N = 2, 150, 384, 64
+    x, dt, A, Bm, Cm, D = FU.scan_inputs(B, L, Di, N, seed=31, structured_a=True)
+    x[:, 10:40, :128] = 0.0                                   # a long run of exact zeros
+    x[:, 50:60, 128:256] *= 1e-25                             # |u| far below the clamp
+    x[:, 70:75, 256:] *= 1e4                                  # large inputs, then back to O(1)
+    x[1, :, ::7] = 0.0                                        # rows that are zero throughout
+    dt[:, 90:95] = 1e-6                                       # tiny step sizes (decay ~ 1)
+    z = rs.standard_normal(x.shape).astype(np.float32)
+    ref = O.selective_scan(x.astype(np.float64), dt.astype(np.float64), A.astype(np.float64), Bm.astype(np.float64),
+                           Cm.astype(np.float64), D.astype(np.float64), mode="sequential") * (z / (1 + np.exp(-z.astype(np.float64))))
+    t = lambda a: torch.from_numpy(a).cuda()
+    got = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="sequential").cpu().numpy()
+    assert np.isfinite(got).all()
+    scale = np.abs(ref).max(axis=(1,), keepdims=True) + 1e-6   # per (batch, channel): rows differ by 1e4 in magnitude
+    assert (np.abs(got - ref) / scale).max() < 1e-4        # the bar of test_scan_oracle, here per channel
+    zero_rows = np.abs(x[1]).max(axis=0) == 0
+    assert np.abs(got[1][:, zero_rows]).max() < 1e-9            # y = 0 (up to the 1e-12 clamp) where x is 0 throughout
+
+
 def test_scan_mamba_signature(va):
     x, dt, A, Bm, Cm, D = FU.scan_inputs(2, 50, 384, 64, 77, True)
     t = lambda a: torch.from_numpy(a).cuda()
