@@ -375,7 +375,7 @@ def run_own_arm(args):
                          "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": local_ms,
                          "scan_launches_per_step": n_scan, "scan_ms_per_step": scan_total_ms,
                          "scan_share_of_step": scan_total_ms / step_total_ms,
-                         "note": "fp32-issue bound, not HBM bound (DESIGN.md): 24,576 state updates x 4 fp32 ops "
+                         "note": "fp32-issue bound, not HBM bound (DESIGN.md): 24,576 state updates x 3 fp32 ops "
                                  "per token-layer"},
             "clocks": clocks,
         }

@@ -125,6 +125,13 @@ int vasr_ctc_greedy_timestamps(const float* logits_dev, int64_t B, int64_t L, in
                                int32_t* tokens_dev, int32_t* starts_dev, int32_t* ends_dev, int32_t* lens_dev,
                                void* stream);
 
+/* ---- ctc_beam_search (velocity_asr/decode.py:128-217), lm_scorer = None
+ * Prefix beam search with the reference's max-merge rule, fp64 scores and insertion-order tie-breaks.
+ * tokens (B, beam_width, L) int32 (-1 padded), lens (B, beam_width) int32 (-1 where the utterance has fewer
+ * beams), scores (B, beam_width) fp64, best beam first.  1 <= beam_width <= 32. */
+int vasr_ctc_beam_search(const float* logits_dev, int64_t B, int64_t L, int64_t V, int beam_width, int blank,
+                         int32_t* tokens_dev, int32_t* lens_dev, double* scores_dev, void* stream);
+
 /* ---- transcribe: load -> mel -> model -> greedy (scripts/transcribe.py:69-82), batched.
  * tokens (B, L) int32, lens (B); L = vasr_num_tokens(vasr_num_frames(S)). */
 int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S,

@@ -554,6 +554,43 @@ def ctc_greedy_decode_with_timestamps(logits, blank_token: int = BLANK_TOKEN):
     return out
 
 
+def log_softmax32(logits):
+    """F.log_softmax in fp32 (decode.py:152): (x - max) - log(sum(exp(x - max)))."""
+    x = np.asarray(logits, dtype=np.float32)
+    sh = x - x.max(axis=-1, keepdims=True)
+    return (sh - np.log(np.exp(sh).sum(axis=-1, keepdims=True, dtype=np.float32))).astype(np.float32)
+
+
+def ctc_beam_search(logits, beam_width: int = 10, blank_token: int = BLANK_TOKEN, log_probs=None):
+    """decode.py:128-217 (lm_scorer=None), restated.  Per utterance a list of (tokens, score), best first.
+    One hypothesis per collapsed prefix; a frame offers every hypothesis the blank (prefix kept), its own last
+    token again (prefix kept) or any other token (prefix grown); equal prefixes keep the better score, the
+    earlier offer on a tie; the `beam_width` best survive, earlier offers first among equals.  Scores are
+    Python floats (fp64) fed with fp32 log-probs.  `log_probs` overrides the fp32 log_softmax (used to hand
+    the oracle the reference's own table)."""
+    lp_all = log_softmax32(logits) if log_probs is None else np.asarray(log_probs)
+    out = []
+    for lp_utt in lp_all:
+        hyps = [((), 0.0, None)]                       # (prefix, score, last token), ranked
+        for lp in lp_utt:
+            offers = {}                                # prefix -> [score, last]; dicts keep first-offer order
+            def offer(prefix, sc, tok):
+                cur = offers.get(prefix)
+                if cur is None:
+                    offers[prefix] = [sc, tok]
+                elif cur[0] < sc:
+                    cur[0], cur[1] = sc, tok
+            for prefix, sc, last in hyps:
+                offer(prefix, sc + float(lp[blank_token]), blank_token)
+                for tok in range(lp.shape[0]):
+                    if tok != blank_token:
+                        offer(prefix if tok == last else prefix + (tok,), sc + float(lp[tok]), tok)
+            ranked = sorted(offers.items(), key=lambda kv: -kv[1][0])[:beam_width]   # stable
+            hyps = [(k, v[0], v[1]) for k, v in ranked]
+        out.append([(list(k), sc) for k, sc, _ in hyps])
+    return out
+
+
 def transcribe(audio, sd, cfg=None, dtype=np.float64) -> List[List[int]]:
     """load->mel->model->greedy, the order of scripts/transcribe.py:69-82."""
     return ctc_greedy_decode(forward(log_mel(audio, dtype=dtype), sd, cfg, dtype))

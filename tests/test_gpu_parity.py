@@ -439,6 +439,51 @@ def test_ctc_timestamps_vs_oracle(va):
         [([5, 5, 7, 3, 5], [(1, 3), (4, 5), (5, 8), (10, 12), (12, 13)])]
 
 
+def test_ctc_beam_search_vs_reference_golden(va, golden):
+    """ctc_beam_search (decode.py:128-217) on the device against outputs of the reference itself
+    (tests/golden/beam.npz): prefixes, beam order and beam count bit-exact — including the cases whose
+    scores tie exactly, where the reference's insertion order decides — and the fp64 scores to the fp32
+    rounding of the log-softmax table (1e-4 absolute over <= 40 frames)."""
+    g = golden("beam")
+    for i in range(int(g["n_cases"])):
+        lg, (W, blank) = g[f"lg_{i}"], g[f"par_{i}"].tolist()
+        res = va.ctc_beam_search(torch.from_numpy(lg).cuda(), beam_width=W, blank_token=blank)
+        want_tok, want_len, want_sc = g[f"tok_{i}"], g[f"len_{i}"], g[f"sc_{i}"]
+        for b, beams in enumerate(res):
+            assert len(beams) == int((want_len[b] >= 0).sum()), (i, b)
+            for r, d in enumerate(beams):
+                assert d.tokens == want_tok[b, r, :want_len[b, r]].tolist(), (i, b, r)
+                assert abs(d.score - want_sc[b, r]) < 1e-4, (i, b, r)
+
+
+def test_ctc_beam_search_vs_oracle_and_greedy(va):
+    """Larger shapes against the oracle (vocab 1000, the default width 10, 60 frames), and the sanity
+    properties: beams are distinct prefixes with non-increasing scores; with peaked frames the best beam is
+    the greedy transcript; the decoder class returns texts of the best beam."""
+    rs = np.random.RandomState(9)
+    lg = (rs.standard_normal((3, 60, 1000)) * 2.5).astype(np.float32)
+    res = va.ctc_beam_search(torch.from_numpy(lg).cuda())
+    want = O.ctc_beam_search(lg, 10)
+    for beams, wb in zip(res, want):
+        assert [d.tokens for d in beams] == [t for t, _ in wb]
+        assert np.allclose([d.score for d in beams], [s for _, s in wb], rtol=0, atol=2e-4)
+        assert len({tuple(d.tokens) for d in beams}) == len(beams) == 10
+        assert all(a.score >= b.score for a, b in zip(beams, beams[1:]))
+    pred = torch.randint(0, 5, (4, 200), generator=torch.Generator().manual_seed(2))
+    pk = (torch.nn.functional.one_hot(pred, 50).float() * 12.0).cuda()
+    best = [utt[0].tokens for utt in va.ctc_beam_search(pk, beam_width=4)]
+    assert best == va.ctc_greedy_decode(pk)
+    dec = va.CTCDecoder(va.create_default_vocabulary(50))
+    assert dec.decode_beam_search(pk, beam_width=4) == dec.decode_greedy(pk)
+    allb = dec.decode_beam_search(pk, beam_width=3, return_all_beams=True)
+    assert len(allb) == 4 and all(len(u) == 3 and isinstance(u[0].text, str) for u in allb)
+    assert va.ctc_beam_search(torch.zeros(2, 0, 7).cuda(), 3)[0][0].tokens == []
+    with pytest.raises(NotImplementedError):
+        va.ctc_beam_search(pk, lm_scorer=object(), lm_weight=0.5)
+    with pytest.raises(ValueError):
+        va.ctc_beam_search(pk, beam_width=33)
+
+
 def test_ctc_greedy_random_vs_oracle(va):
     g = torch.Generator().manual_seed(4)
     pred = torch.randint(0, 4, (7, 1003), generator=g)           # many blanks and repeats, ragged outputs

@@ -120,6 +120,33 @@ def test_decode_known_answers(golden):
     assert O.ctc_greedy_decode(np.zeros((2, 0, 5))) == [[], []]
 
 
+def _beam_arrays(res, W, L):
+    tok = np.full((len(res), W, L), -1, np.int32)
+    ln = np.full((len(res), W), -1, np.int32)
+    sc = np.full((len(res), W), -np.inf)
+    for b, beams in enumerate(res):
+        for r, (t, s) in enumerate(beams):
+            ln[b, r], sc[b, r] = len(t), s
+            tok[b, r, :len(t)] = t
+    return tok, ln, sc
+
+
+def test_beam_search_matches_reference(golden):
+    """ctc_beam_search (decode.py:128-217): with the reference's own log-prob table the restatement is
+    bit-exact (prefixes, ranking, fp64 scores); with its own fp32 log_softmax the prefixes and ranking are
+    the same and the scores agree to fp32 rounding of the table."""
+    g = golden("beam")
+    for i in range(int(g["n_cases"])):
+        lg, (W, blank) = g[f"lg_{i}"], g[f"par_{i}"].tolist()
+        tok, ln, sc = _beam_arrays(O.ctc_beam_search(lg, W, blank, log_probs=g[f"lp_{i}"]), W, lg.shape[1])
+        assert np.array_equal(tok, g[f"tok_{i}"]) and np.array_equal(ln, g[f"len_{i}"]), i
+        assert np.array_equal(sc, g[f"sc_{i}"]), i
+        tok, ln, sc = _beam_arrays(O.ctc_beam_search(lg, W, blank), W, lg.shape[1])
+        assert np.array_equal(tok, g[f"tok_{i}"]) and np.array_equal(ln, g[f"len_{i}"]), i
+        assert np.allclose(sc, g[f"sc_{i}"], rtol=0, atol=1e-4), i
+    assert O.ctc_beam_search(np.zeros((2, 0, 5), np.float32), 4) == [[([], 0.0)], [([], 0.0)]]
+
+
 def test_fake_quantize_arithmetic():
     x = np.array([[-1.0, 0.26, 0.5], [2.0, -0.1, 0.05]])
     s, zp = O.fake_quant_params(x, symmetric=True, per_channel=True)

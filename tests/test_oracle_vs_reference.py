@@ -67,3 +67,14 @@ def test_timestamp_decode_matches_reference():
         lg = np.repeat(lg, 2, axis=1)[:, :L]
         ref = R.decode.ctc_greedy_decode_with_timestamps(torch.from_numpy(lg))
         assert [(list(t), [tuple(x) for x in s]) for t, s in ref] == O.ctc_greedy_decode_with_timestamps(lg)
+
+
+def test_beam_search_matches_reference():
+    """decode.py:128-217 run live against the restatement fed with the reference's log-prob table."""
+    rs = np.random.RandomState(5)
+    for (B, L, V, W, blank) in [(2, 18, 9, 4, 0), (1, 10, 4, 6, 1), (2, 9, 7, 1, 0), (1, 14, 5, 3, 4)]:
+        lg = (np.round(rs.standard_normal((B, L, V)) * 3.0) / 3.0).astype(np.float32)
+        ref = R.decode.ctc_beam_search(torch.from_numpy(lg), beam_width=W, blank_token=blank)
+        lp = torch.log_softmax(torch.from_numpy(lg), dim=-1).numpy()
+        got = O.ctc_beam_search(lg, W, blank, log_probs=lp)
+        assert [[(d.tokens, d.score) for d in utt] for utt in ref] == got

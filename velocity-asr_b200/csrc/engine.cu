@@ -1047,6 +1047,31 @@ int vasr_ctc_greedy_timestamps(const float* logits_dev, int64_t B, int64_t L, in
   return VASR_OK;
 }
 
+int vasr_ctc_beam_search(const float* logits_dev, int64_t B, int64_t L, int64_t V, int beam_width, int blank,
+                         int32_t* tokens_dev, int32_t* lens_dev, double* scores_dev, void* stream) {
+  if (!tokens_dev && B * beam_width * L > 0) return fail(VASR_ERR_INVALID, "null argument");
+  if (!lens_dev || !scores_dev || (!logits_dev && B * L > 0)) return fail(VASR_ERR_INVALID, "null argument");
+  if (beam_width < 1 || beam_width > 32) return fail(VASR_ERR_INVALID, "beam_width must be in [1, 32]");
+  if (V < 1 || blank < 0 || blank >= V) return fail(VASR_ERR_INVALID, "blank token outside the vocabulary");
+  if (B <= 0) return VASR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int W = beam_width;
+  const int K = (int)(V - 1 < W + 1 ? V - 1 : W + 1) > 0 ? (int)(V - 1 < W + 1 ? V - 1 : W + 1) : 1;
+  const int64_t M = B * L, cap = 1 + L * W;
+  float2* stats = nullptr;
+  int32_t *top = nullptr, *trie = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&stats), (size_t)(M > 0 ? M : 1) * sizeof(float2), s));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&top), (size_t)(M > 0 ? M : 1) * K * sizeof(int32_t), s));
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&trie), (size_t)3 * B * cap * sizeof(int32_t), s));
+  KL(launch_beam_rows(logits_dev, stats, top, M, (int)V, K, blank, s, nullptr));
+  KL(launch_beam_search(logits_dev, stats, top, K, B, L, (int)V, W, blank, trie, cap, tokens_dev, lens_dev,
+                        scores_dev, s, nullptr));
+  CK(cudaFreeAsync(stats, s));
+  CK(cudaFreeAsync(top, s));
+  CK(cudaFreeAsync(trie, s));
+  return VASR_OK;
+}
+
 static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pcm_host, int64_t B, int64_t S,
                            int32_t* tokens_dev, int32_t* lens_dev, int32_t* tokens_host, int32_t* lens_host,
                            cudaStream_t s) {

@@ -12,7 +12,8 @@ __version__ = "2.0.0+b200"
 from .config import VelocityASRConfig, config_from_yaml, SCAN_MODES
 from .engine import VELOCITYASR
 from .frontend import compute_mel_spectrogram, SAMPLE_RATE, N_FFT, HOP_LENGTH, N_MELS
-from .ctc import (ctc_greedy_decode, ctc_greedy_decode_with_timestamps, CTCDecoder, create_default_vocabulary,
+from .ctc import (ctc_greedy_decode, ctc_greedy_decode_with_timestamps, ctc_beam_search, DecodingResult, CTCDecoder,
+                  create_default_vocabulary,
                   BLANK_TOKEN)
 from .ops import selective_scan, selective_scan_fn, linear, split_tf32
 from .quantize import QuantizationConfig, prepare_model_for_qat, calibrate_model
@@ -28,7 +29,7 @@ def from_pretrained(model_name_or_path: str, **kwargs) -> VELOCITYASR:
 __all__ = [
     "__version__", "VELOCITYASR", "VelocityASRConfig", "config_from_yaml", "from_pretrained",
     "compute_mel_spectrogram", "SAMPLE_RATE", "N_FFT", "HOP_LENGTH", "N_MELS",
-    "ctc_greedy_decode", "ctc_greedy_decode_with_timestamps", "CTCDecoder", "create_default_vocabulary", "BLANK_TOKEN",
+    "ctc_greedy_decode", "ctc_greedy_decode_with_timestamps", "ctc_beam_search", "DecodingResult", "CTCDecoder", "create_default_vocabulary", "BLANK_TOKEN",
     "selective_scan", "selective_scan_fn", "linear", "split_tf32", "MAMBA_AVAILABLE", "SCAN_MODES",
     "QuantizationConfig", "prepare_model_for_qat", "calibrate_model",
 ]

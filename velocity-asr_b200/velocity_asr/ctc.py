@@ -1,7 +1,8 @@
 """CTC decoding: ctc_greedy_decode / CTCDecoder / create_default_vocabulary of
 velocity_asr/decode.py, with the argmax and the blank/repeat collapse done on the GPU."""
 import ctypes
-from typing import List, Tuple
+from dataclasses import dataclass
+from typing import Any, List, Optional, Tuple
 
 import torch
 
@@ -62,8 +63,49 @@ def ctc_greedy_decode_with_timestamps(logits: torch.Tensor, blank_token: int = B
             for b, n in enumerate(lens)]
 
 
+@dataclass
+class DecodingResult:
+    """decode.py:17-24."""
+
+    text: str
+    tokens: List[int]
+    score: float
+    timestamps: Optional[List[Tuple[int, int]]] = None
+
+
+def ctc_beam_search(logits: torch.Tensor, beam_width: int = 10, blank_token: int = BLANK_TOKEN,
+                    lm_weight: float = 0.0, lm_scorer: Optional[Any] = None) -> List[List[DecodingResult]]:
+    """decode.py:128-217 on the GPU: per utterance the `beam_width` best prefixes, best first, with the
+    reference's rule (log_softmax; blank / repeated token keep the prefix, any other token extends it; equal
+    prefixes keep the better score; fp64 score sums; ties in insertion order).  A Python `lm_scorer` cannot
+    run inside the device loop and is refused rather than silently ignored."""
+    if lm_scorer is not None and lm_weight > 0:
+        raise NotImplementedError("velocity_asr (B200 build): ctc_beam_search runs on the device and takes no "
+                                  "Python lm_scorer")
+    if logits.dim() != 3:
+        raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
+    if logits.device.type != "cuda":
+        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    B, L, V = logits.shape
+    W = int(beam_width)
+    if B == 0:
+        return []
+    lg = logits.to(torch.float32).contiguous()
+    tokens = torch.empty(B, W, max(L, 1), dtype=torch.int32, device=lg.device)
+    lens = torch.empty(B, W, dtype=torch.int32, device=lg.device)
+    scores = torch.empty(B, W, dtype=torch.float64, device=lg.device)
+    lib = _native.lib()
+    with torch.cuda.device(lg.device):
+        _native.check(lib.vasr_ctc_beam_search(
+            _native.ptr(lg), B, L, V, W, int(blank_token), _native.ptr(tokens), _native.ptr(lens),
+            _native.ptr(scores), ctypes.c_void_p(torch.cuda.current_stream(lg.device).cuda_stream)))
+    tokens, lens, scores = tokens.cpu().numpy(), lens.cpu().tolist(), scores.cpu().tolist()
+    return [[DecodingResult(text="", tokens=tokens[b, r, :n].tolist(), score=scores[b][r])
+             for r, n in enumerate(lens[b]) if n >= 0] for b in range(B)]
+
+
 class CTCDecoder:
-    """decode.py:220-328 (greedy path): vocabulary lookup around ctc_greedy_decode."""
+    """decode.py:220-328: vocabulary lookup around the greedy and beam-search decoders."""
 
     def __init__(self, vocabulary: List[str], blank_token: int = BLANK_TOKEN):
         self.vocabulary = vocabulary
@@ -74,6 +116,16 @@ class CTCDecoder:
     def decode_greedy(self, logits: torch.Tensor, collapse_repeated: bool = True) -> List[str]:
         seqs = ctc_greedy_decode(logits, blank_token=self.blank_token, collapse_repeated=collapse_repeated)
         return [self._tokens_to_text(s) for s in seqs]
+
+    def decode_beam_search(self, logits: torch.Tensor, beam_width: int = 10, return_all_beams: bool = False):
+        """decode.py:265-300: best-beam texts, or every beam with its text filled in."""
+        beams = ctc_beam_search(logits, beam_width=beam_width, blank_token=self.blank_token)
+        if return_all_beams:
+            for utt in beams:
+                for r in utt:
+                    r.text = self._tokens_to_text(r.tokens)
+            return beams
+        return [self._tokens_to_text(utt[0].tokens) if utt else "" for utt in beams]
 
     def _tokens_to_text(self, tokens: List[int]) -> str:
         """decode.py:302-317: join, then turn the subword marker into spaces."""
