@@ -125,6 +125,21 @@ int vasr_ctc_greedy_timestamps(const float* logits_dev, int64_t B, int64_t L, in
                                int32_t* tokens_dev, int32_t* starts_dev, int32_t* ends_dev, int32_t* lens_dev,
                                void* stream);
 
+/* ---- ragged batches (the reference's collator pads with zeros and never masks, data.py:145-203, so an
+ * utterance's transcript depends on its batch mates; these entry points take the true lengths instead)
+ * pcm (B, S) holds utterance b in its first sample_lens[b] samples (200 < len <= S; the rest is ignored).
+ * Each utterance is processed exactly as if it were alone: reflect padding, frame count and mel statistics from
+ * its own length, zero frames after its end, pooling windows and attention keys from its own token count, decode
+ * over its own tokens.  tokens (B, L) / lens (B) as vasr_transcribe, L = vasr_num_tokens(vasr_num_frames(S)).
+ * sample_lens / frame_lens are HOST arrays.  vasr_forward_ragged: mel (B, T, n_mels) with frame_lens[b] valid
+ * frames (1 <= len <= T); logits rows at or past an utterance's own token count are padding. */
+int vasr_transcribe_ragged(vasr_handle* h, const float* pcm_dev, const int32_t* sample_lens_host, int64_t B,
+                           int64_t S, int32_t* tokens_dev, int32_t* lens_dev, void* stream);
+int vasr_transcribe_ragged_host(vasr_handle* h, const float* pcm_host, const int32_t* sample_lens_host, int64_t B,
+                                int64_t S, int32_t* tokens_host, int32_t* lens_host);
+int vasr_forward_ragged(vasr_handle* h, const float* mel_dev, const int32_t* frame_lens_host, int64_t B, int64_t T,
+                        float* logits_dev, void* stream);
+
 /* ---- ctc_beam_search (velocity_asr/decode.py:128-217), lm_scorer = None
  * Prefix beam search with the reference's max-merge rule, fp64 scores and insertion-order tie-breaks.
  * tokens (B, beam_width, L) int32 (-1 padded), lens (B, beam_width) int32 (-1 where the utterance has fewer

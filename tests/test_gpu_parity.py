@@ -332,6 +332,45 @@ def test_transcribe_list_and_trainer_checkpoint(va, tmp_path):
     assert torch.equal(loaded(mel), small.cuda().eval()(mel))
 
 
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_ragged_batch_equals_each_utterance_alone(va, mode):
+    """f3 of SURVEY 8f, the masked mode: one padded batch with per-utterance lengths gives every utterance
+    bit for bit what it gets alone — logits and tokens — whatever sits in the padding.  Lengths cover every
+    branch of the pooling sizes (K1 = L | 64 | L/8, K2 = 16 | K1/4) and odd sample counts."""
+    m = make_model(va, mode, amp=True)
+    lens = [16000, 4800, 240000, 96000, 23457, 201 + 160, 240000]
+    S = max(lens)
+    g = torch.Generator().manual_seed(5)
+    pcm = torch.randn(len(lens), S, generator=g) * 0.3                 # the padding is noise, not zeros
+    for b, n in enumerate(lens):
+        pcm[b, :n] = FU.synth_audio(1, n, seed=60 + b)[0]
+    alone = [m.transcribe(pcm[b, :n].cuda())[0] for b, n in enumerate(lens)]
+    assert m.transcribe(pcm.cuda(), lengths=lens) == alone
+    assert m.transcribe(pcm.pin_memory(), lengths=torch.tensor(lens)) == alone      # host entry point
+    host = pcm.pin_memory()
+    assert list(m.transcribe_batches([(host, lens), host[:2, :16000], (host, lens)])) == \
+        [alone, m.transcribe(host[:2, :16000]), alone]                               # pipelined, mixed with plain
+    assert any(len(t) > 0 for t in alone)
+    # forward with frame counts: logits rows of the valid tokens are identical, padding content is ignored
+    mels = [va.compute_mel_spectrogram(pcm[b, :n].cuda()) for b, n in enumerate(lens)]
+    T = max(x.shape[0] for x in mels)
+    batch = torch.full((len(lens), T, 80), 7.0, device="cuda")
+    for b, x in enumerate(mels):
+        batch[b, :x.shape[0]] = x
+    out = m(batch, lengths=[x.shape[0] for x in mels])
+    for b, x in enumerate(mels):
+        want = m(x.unsqueeze(0))[0]
+        assert torch.equal(out[b, :want.shape[0]], want), (mode, b)
+    # full-length utterances in a ragged call are the plain call
+    assert torch.equal(m(batch[[2, 6]], lengths=[T, T]), m(batch[[2, 6]]))
+    with pytest.raises(RuntimeError):
+        m.transcribe(pcm.cuda(), lengths=[200] + lens[1:])
+    with pytest.raises(RuntimeError):
+        m.transcribe(pcm.cuda(), lengths=[S + 1] + lens[1:])
+    with pytest.raises(RuntimeError):
+        m.transcribe(pcm.cuda(), lengths=lens[1:])
+
+
 def test_long_form_needs_longer_table(va):
     m = make_model(va, "sequential")
     mel = torch.randn(1, 10003, 80, device="cuda")      # 5002 tokens > pe_time rows (model.py:87,125)

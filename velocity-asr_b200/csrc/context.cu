@@ -12,10 +12,17 @@ namespace {
 // F.adaptive_avg_pool1d: window i = [floor(i L / K), ceil((i+1) L / K))
 __global__ void __launch_bounds__(256) adaptive_pool_kernel(const float* __restrict__ x, int64_t ldx,
                                                             float* __restrict__ out, int64_t L, int64_t K,
-                                                            int C) {
+                                                            int C, const int32_t* __restrict__ rag, int f_in,
+                                                            int f_out) {
   const int64_t i = blockIdx.x, b = blockIdx.y;
-  const int64_t s = (i * L) / K;
-  const int64_t e = ((i + 1) * L + K - 1) / K;
+  const int64_t Lb = rag ? rag[b * RAG_STRIDE + f_in] : L;      // rows keep the strides of L and K
+  const int64_t Kb = rag ? rag[b * RAG_STRIDE + f_out] : K;
+  if (i >= Kb) {
+    for (int c = threadIdx.x; c < C; c += 256) out[(b * K + i) * C + c] = 0.f;
+    return;
+  }
+  const int64_t s = (i * Lb) / Kb;
+  const int64_t e = ((i + 1) * Lb + Kb - 1) / Kb;
   const float inv = 1.0f / (float)(e - s);
   for (int c = threadIdx.x; c < C; c += 256) {
     float acc = 0.f;
@@ -30,11 +37,14 @@ constexpr int ATT_TOK = 64;
 constexpr int ATT_MAX_HD = 16;
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int64_t ldq,
                                                         const float* __restrict__ kv, float* __restrict__ o,
-                                                        int64_t ldo, int64_t L, int64_t Kk, int heads, int hd) {
+                                                        int64_t ldo, int64_t L, int64_t Kk, int heads, int hd,
+                                                        const int32_t* __restrict__ rag) {
   extern __shared__ float skv[];  // Kk x (2*A)
   const int A = heads * hd;
   const int64_t b = blockIdx.y;
-  for (int idx = threadIdx.x; idx < Kk * 2 * A; idx += blockDim.x) skv[idx] = kv[b * Kk * 2 * A + idx];
+  const float* kvb = kv + b * Kk * 2 * A;
+  if (rag) Kk = rag[b * RAG_STRIDE + RAG_K2];    // ragged: this utterance has fewer pooled keys
+  for (int idx = threadIdx.x; idx < Kk * 2 * A; idx += blockDim.x) skv[idx] = kvb[idx];
   __syncthreads();
   const int tok = threadIdx.x / heads, hh = threadIdx.x % heads;
   const int64_t t = (int64_t)blockIdx.x * ATT_TOK + tok;
@@ -146,23 +156,25 @@ cudaError_t launch_set_qparams(const float* mm, float* q_scale, float* q_zp, int
 }
 
 cudaError_t launch_adaptive_pool(const float* x, int64_t ldx, float* out, int64_t B, int64_t L, int64_t K,
-                                 int C, cudaStream_t s, int64_t* launches) {
+                                 int C, cudaStream_t s, int64_t* launches, const int32_t* rag, int f_in,
+                                 int f_out) {
   if (B <= 0 || K <= 0) return cudaSuccess;
   if (B > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)K, (unsigned)B);
-  adaptive_pool_kernel<<<grid, 256, 0, s>>>(x, ldx, out, L, K, C);
+  adaptive_pool_kernel<<<grid, 256, 0, s>>>(x, ldx, out, L, K, C, rag, f_in, f_out);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
 
 cudaError_t launch_attention(const float* q, int64_t ldq, const float* kv, float* o, int64_t ldo, int64_t B,
-                             int64_t L, int64_t Kk, int heads, int hd, cudaStream_t s, int64_t* launches) {
+                             int64_t L, int64_t Kk, int heads, int hd, cudaStream_t s, int64_t* launches,
+                             const int32_t* rag) {
   if (B <= 0 || L <= 0) return cudaSuccess;
   if (hd > ATT_MAX_HD || heads * ATT_TOK > 1024 || B > 65535) return cudaErrorInvalidValue;
   const size_t smem = (size_t)Kk * 2 * heads * hd * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((L + ATT_TOK - 1) / ATT_TOK), (unsigned)B);
-  attention_kernel<<<grid, heads * ATT_TOK, smem, s>>>(q, ldq, kv, o, ldo, L, Kk, heads, hd);
+  attention_kernel<<<grid, heads * ATT_TOK, smem, s>>>(q, ldq, kv, o, ldo, L, Kk, heads, hd, rag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -42,17 +42,19 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
 // so comparing with the raw predecessor is the same rule, decode.py:55-66.)
 __global__ void __launch_bounds__(32) ctc_collapse_kernel(const int32_t* __restrict__ pred,
                                                           int32_t* __restrict__ tokens, int32_t* __restrict__ lens,
-                                                          int64_t L, int blank, int collapse) {
+                                                          int64_t L, int blank, int collapse,
+                                                          const int32_t* __restrict__ rag) {
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x;
   const int32_t* p = pred + b * L;
   int32_t* out = tokens + b * L;
+  const int64_t Lb = rag ? rag[b * RAG_STRIDE + RAG_L] : L;   // ragged: tokens past the utterance's end are padding
   int count = 0;
-  for (int64_t t0 = 0; t0 < L; t0 += 32) {
+  for (int64_t t0 = 0; t0 < Lb; t0 += 32) {
     const int64_t t = t0 + lane;
     int tok = blank;
     bool keep = false;
-    if (t < L) {
+    if (t < Lb) {
       tok = p[t];
       keep = tok != blank && (!collapse || t == 0 || tok != p[t - 1]);
     }
@@ -121,9 +123,9 @@ cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, 
 }
 
 cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
-                                int blank, int collapse, cudaStream_t s, int64_t* launches) {
+                                int blank, int collapse, cudaStream_t s, int64_t* launches, const int32_t* rag) {
   if (B <= 0) return cudaSuccess;
-  ctc_collapse_kernel<<<(unsigned)B, 32, 0, s>>>(pred, tokens, lens, L, blank, collapse);
+  ctc_collapse_kernel<<<(unsigned)B, 32, 0, s>>>(pred, tokens, lens, L, blank, collapse, rag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -88,6 +88,13 @@ struct vasr_handle {
   int quant_active = 0;      // the committed weights are fake-quantised and the sites below exist
   int calibrating = 0;       // this forward updates the activation scales before using them
   QSite qsite[Q_SITES];
+  // pinned staging of a ragged batch's per-utterance dims: a ring, so a call never waits for the stream unless
+  // all RAG_RING earlier uploads are still queued
+  static constexpr int RAG_RING = 4;
+  int32_t* rag_pin[RAG_RING] = {};
+  cudaEvent_t rag_ev[RAG_RING] = {};
+  int64_t rag_pin_cap = 0;
+  int rag_next = 0;
   float* q_mm = nullptr;     // (2) min / max scratch
   // TF32 hi/lo split of each weight matrix the tensor-core kernel has used, keyed by the fp32 copy
   std::unordered_map<const float*, float*> w_split;
@@ -171,6 +178,8 @@ struct Work {
   int32_t* pred;
   float* pcm_stage;      // device copies for the *_host entry points
   int32_t *tok_stage, *len_stage;
+  int32_t* ragbuf;       // B x RAG_STRIDE per-utterance dims of a ragged batch (kernels.cuh)
+  const int32_t* rag;    // = ragbuf for a ragged call, NULL otherwise
 };
 
 // Carves the arena; with measure_only it just computes the size.
@@ -212,6 +221,7 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   if (need_logits) t.logits = a.take<float>(q.M * q.V);
   if (h->quant_active) t.qscratch = a.take<float>(q.M * (q.V > 3 * q.d ? q.V : 3 * q.d));
   t.pred = a.take<int32_t>(q.M);
+  t.ragbuf = a.take<int32_t>(q.B * RAG_STRIDE);
   if (need_stage) {
     t.pcm_stage = a.take<float>(q.B * q.S);
     t.tok_stage = a.take<int32_t>(q.M);
@@ -594,19 +604,19 @@ int quirk_for(const vasr_handle* h, int stack, int scan_mode) {
 // HierarchicalGlobalContext.forward on local features already in k.cat[:, :d] -> k.fused
 int run_global_context(vasr_handle* h, const Dims& q, const Work& k, cudaStream_t s) {
   const int d = q.d, att = q.att;
-  KL(launch_adaptive_pool(k.cat, 2 * d, k.gb, q.B, q.L, q.K1, d, s, &h->launches));
+  KL(launch_adaptive_pool(k.cat, 2 * d, k.gb, q.B, q.L, q.K1, d, s, &h->launches, k.rag, RAG_L, RAG_K1));
   RET(linear(h, k.gb, d, h->p1_w, h->p1_b, k.ga, d, q.Mg, d, d, ACT_NONE, 0, nullptr, 0, s, Q_P1, k.qscratch));
   for (size_t i = 0; i < h->global.size(); ++i)
     RET(run_block(h, h->global[i], k, k.ga, k.gb, q.B, q.K1, quirk_for(h, 1, -1), s));
   KL(launch_layer_norm(k.ga, d, k.ga, d, h->glo_g, h->glo_b, q.Mg, d, s, &h->launches));
-  KL(launch_adaptive_pool(k.ga, d, k.g2, q.B, q.K1, q.K2, d, s, &h->launches));
+  KL(launch_adaptive_pool(k.ga, d, k.g2, q.B, q.K1, q.K2, d, s, &h->launches, k.rag, RAG_K1, RAG_K2));
   RET(linear(h, k.g2, d, h->p2_w, h->p2_b, k.g2n, d, q.M2, d, d, ACT_NONE, 0, nullptr, 0, s, Q_P2, k.qscratch));
   KL(launch_layer_norm(k.g2n, d, k.g2n, d, h->n1_g, h->n1_b, q.M2, d, s, &h->launches));
   RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s, Q_KV, k.qscratch));
   KL(launch_layer_norm(k.cat, 2 * d, k.u, d, h->n2_g, h->n2_b, q.M, d, s, &h->launches));
   RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s, Q_Q, k.qscratch));
   KL(launch_attention(k.qb, att, k.kv, k.ob, att, q.B, q.L, q.K2, h->cfg.attention_heads,
-                      att / h->cfg.attention_heads, s, &h->launches));
+                      att / h->cfg.attention_heads, s, &h->launches, k.rag));
   RET(linear(h, k.ob, att, h->w_o, h->b_o, k.cat + d, 2 * d, q.M, att, d, ACT_NONE, 0, nullptr, 0, s, Q_O, k.qscratch));
   RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s, Q_F3, k.qscratch));
   KL(launch_gate_mix(k.f3, k.fm, q.M, d, s, &h->launches));
@@ -652,10 +662,12 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
 int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int normalize, cudaStream_t s) {
   if (!h->mel_dft) {
     KL(launch_mel_fft(pcm, k.raw, normalize ? k.part : nullptr, q.B, q.S, q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w,
-                      h->win, h->tw400, s, &h->launches));
-    if (normalize) KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches));
+                      h->win, h->tw400, s, &h->launches, k.rag));
+    if (normalize)
+      KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
     return VASR_OK;
   }
+  if (k.rag) return fail(VASR_ERR_UNSUPPORTED, "ragged batches need the FFT mel path (unset VASR_MEL=dft)");
   KL(launch_reflect_pad(pcm, k.xp, q.B, q.S, PAD, q.ldp, s, &h->launches));
   GemmArgs g;
   g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
@@ -808,6 +820,10 @@ void vasr_destroy(vasr_handle* h) {
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int i = 0; i < vasr_handle::RAG_RING; ++i) {
+    if (h->rag_pin[i]) cudaFreeHost(h->rag_pin[i]);
+    if (h->rag_ev[i]) cudaEventDestroy(h->rag_ev[i]);
+  }
   delete h;
 }
 
@@ -1072,13 +1088,56 @@ int vasr_ctc_beam_search(const float* logits_dev, int64_t B, int64_t L, int64_t 
   return VASR_OK;
 }
 
+// Per-utterance dims of a ragged batch -> k.ragbuf, k.rag.  `lens` (host) are samples (from_samples) or mel
+// frames; each utterance gets the dims make_dims would give it alone.
+static int upload_ragged(vasr_handle* h, const Dims& q, Work& k, const int32_t* lens, bool from_samples,
+                         cudaStream_t s) {
+  const int64_t count = q.B * RAG_STRIDE;
+  if (count > h->rag_pin_cap) {
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < vasr_handle::RAG_RING; ++i) {
+      if (h->rag_pin[i]) CK(cudaFreeHost(h->rag_pin[i]));
+      h->rag_pin[i] = nullptr;
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&h->rag_pin[i]), (size_t)count * sizeof(int32_t), cudaHostAllocDefault));
+      if (!h->rag_ev[i]) CK(cudaEventCreateWithFlags(&h->rag_ev[i], cudaEventDisableTiming));
+    }
+    h->rag_pin_cap = count;
+  }
+  const int slot = h->rag_next;
+  h->rag_next = (slot + 1) % vasr_handle::RAG_RING;
+  CK(cudaEventSynchronize(h->rag_ev[slot]));      // the upload that last used this slot has been consumed
+  int32_t* host = h->rag_pin[slot];
+  for (int64_t i = 0; i < count; ++i) host[i] = 0;
+  for (int64_t b = 0; b < q.B; ++b) {
+    const int64_t n = lens[b];
+    if (from_samples) {
+      if (n <= PAD || n > q.S)
+        return fail(VASR_ERR_SHAPE, "ragged batch: every utterance needs more than 200 and at most S samples");
+    } else if (n < 1 || n > q.T) {
+      return fail(VASR_ERR_SHAPE, "ragged batch: every utterance needs between 1 and T frames");
+    }
+    const Dims u = make_dims(h, 1, from_samples ? n : 0, from_samples ? vasr_num_frames(n) : n);
+    int32_t* r = host + b * RAG_STRIDE;
+    r[RAG_S] = (int32_t)(from_samples ? n : 0);
+    r[RAG_T] = (int32_t)u.T;
+    r[RAG_L] = (int32_t)u.L;
+    r[RAG_K1] = (int32_t)u.K1;
+    r[RAG_K2] = (int32_t)u.K2;
+  }
+  CK(cudaMemcpyAsync(k.ragbuf, host, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(h->rag_ev[slot], s));
+  k.rag = k.ragbuf;
+  return VASR_OK;
+}
+
 static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pcm_host, int64_t B, int64_t S,
                            int32_t* tokens_dev, int32_t* lens_dev, int32_t* tokens_host, int32_t* lens_host,
-                           cudaStream_t s) {
+                           cudaStream_t s, const int32_t* sample_lens = nullptr) {
   const bool host = pcm_host != nullptr;
   const Dims q = make_dims(h, B, S, vasr_num_frames(S));
   Work k;
   RET(ensure_workspace(h, q, true, true, &k, host));
+  if (sample_lens) RET(upload_ragged(h, q, k, sample_lens, true, s));
   if (host) {
     CK(cudaMemcpyAsync(k.pcm_stage, pcm_host, (size_t)B * S * sizeof(float), cudaMemcpyHostToDevice, s));
     pcm_dev = k.pcm_stage;
@@ -1087,10 +1146,10 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
   }
   timing_begin(h, s);
   RET(run_mel(h, q, k, pcm_dev, 1, s));
-  KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches));
+  KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag));
   RET(run_model(h, q, k, k.logits, nullptr, nullptr, nullptr, s));
   KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));
-  KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches));
+  KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches, k.rag));
   timing_end(h, s);
   if (host) {
     CK(cudaMemcpyAsync(tokens_host, tokens_dev, (size_t)q.M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -1117,6 +1176,45 @@ int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
   RET(bind_device(h));
   return transcribe_impl(h, nullptr, pcm_host, B, S, nullptr, nullptr, tokens_host, lens_host, h->own_stream);
+}
+
+int vasr_transcribe_ragged(vasr_handle* h, const float* pcm_dev, const int32_t* sample_lens_host, int64_t B,
+                           int64_t S, int32_t* tokens_dev, int32_t* lens_dev, void* stream) {
+  RET(check_ready(h));
+  if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev || !sample_lens_host)
+    return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
+  RET(bind_device(h));
+  return transcribe_impl(h, pcm_dev, nullptr, B, S, tokens_dev, lens_dev, nullptr, nullptr,
+                         static_cast<cudaStream_t>(stream), sample_lens_host);
+}
+
+int vasr_transcribe_ragged_host(vasr_handle* h, const float* pcm_host, const int32_t* sample_lens_host, int64_t B,
+                                int64_t S, int32_t* tokens_host, int32_t* lens_host) {
+  RET(check_ready(h));
+  if (B <= 0 || !pcm_host || !tokens_host || !lens_host || !sample_lens_host)
+    return fail(VASR_ERR_INVALID, "null argument");
+  if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
+  RET(bind_device(h));
+  return transcribe_impl(h, nullptr, pcm_host, B, S, nullptr, nullptr, tokens_host, lens_host, h->own_stream,
+                         sample_lens_host);
+}
+
+int vasr_forward_ragged(vasr_handle* h, const float* mel_dev, const int32_t* frame_lens_host, int64_t B, int64_t T,
+                        float* logits_dev, void* stream) {
+  RET(check_ready(h));
+  if (B < 0 || T < 1 || !mel_dev || !logits_dev || !frame_lens_host) return fail(VASR_ERR_INVALID, "null argument");
+  RET(bind_device(h));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims q = make_dims(h, B, 0, T);
+  Work k;
+  RET(ensure_workspace(h, q, false, false, &k));
+  RET(upload_ragged(h, q, k, frame_lens_host, false, s));
+  timing_begin(h, s);
+  KL(launch_mel_finish(mel_dev, nullptr, nullptr, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag));
+  RET(run_model(h, q, k, logits_dev, nullptr, nullptr, nullptr, s));
+  timing_end(h, s);
+  return VASR_OK;
 }
 
 int vasr_linear(const float* x_dev, int64_t ldx, const float* w_dev, const float* bias_dev, float* out_dev,

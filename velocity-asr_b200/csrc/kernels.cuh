@@ -80,6 +80,14 @@ struct ScanArgs {
 };
 cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* launches);
 
+// ---------------------------------------------------------------- ragged batches ---------
+// A batch whose utterances have different lengths is stored padded to the longest; `rag` (device,
+// B x RAG_STRIDE int32) holds what each utterance really has.  Everything along time is causal or
+// per-token except the five places that take `rag`: the reflect padding and frame count of the mel,
+// its statistics, the zero frames after the end, both adaptive poolings, the number of attention keys
+// and the decode length.  NULL = every utterance spans the full rows.
+enum { RAG_S = 0, RAG_T = 1, RAG_L = 2, RAG_K1 = 3, RAG_K2 = 4, RAG_STRIDE = 8 };
+
 // ---------------------------------------------------------------- log-mel front end -----
 // One pass PCM (B, S) -> raw (B, T, n_mels) = log(mel power + 1e-10): reflect padding by index, window,
 // 400-point FFT, power, band-sparse filterbank (weights fb_w[fb_off[j] .. fb_off[j+1]) on frequency bins
@@ -88,10 +96,10 @@ cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* la
 int64_t mel_fft_blocks(int64_t T);
 cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B, int64_t S, int64_t T, int n_mels,
                            const int* fb_lo, const int* fb_off, const float* fb_w, const float* win,
-                           const float* tw, cudaStream_t s, int64_t* launches);
+                           const float* tw, cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr);
 // per (b, j): mean and 1/(unbiased std + 1e-10) over the T frames, from the partials above.
 cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
-                                     cudaStream_t s, int64_t* launches);
+                                     cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr);
 // xp[b, i] = pcm[b, reflect(i - pad)], i in [0, S + 2 pad); row stride ldp.
 cudaError_t launch_reflect_pad(const float* pcm, float* xp, int64_t B, int64_t S, int pad, int64_t ldp,
                                cudaStream_t s, int64_t* launches);
@@ -108,15 +116,18 @@ cudaError_t launch_mel_stats(const float* raw, float* mean, float* rstd, int64_t
 // out has frames_per_utt rows per utterance; rows outside [front, front + T) are zeroed.
 cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* rstd, float* out, int64_t B,
                               int64_t T, int n_mels, int64_t frames_per_utt, int front, cudaStream_t s,
-                              int64_t* launches);
+                              int64_t* launches, const int32_t* rag = nullptr);
 
 // ---------------------------------------------------------------- global context --------
 // out[b, i, :] = mean_t x[b, floor(iL/K) .. ceil((i+1)L/K), :]   (attention.py:71-73)
+// ragged: the input length is rag[b][f_in] and the output count rag[b][f_out] (rows past it are zeroed)
 cudaError_t launch_adaptive_pool(const float* x, int64_t ldx, float* out, int64_t B, int64_t L, int64_t K,
-                                 int C, cudaStream_t s, int64_t* launches);
+                                 int C, cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr,
+                                 int f_in = 0, int f_out = 0);
 // q (B*L, heads*hd) stride ldq; kv (B*Kk, 2*heads*hd): [k | v]; o (B*L, heads*hd) stride ldo.
 cudaError_t launch_attention(const float* q, int64_t ldq, const float* kv, float* o, int64_t ldo, int64_t B,
-                             int64_t L, int64_t Kk, int heads, int hd, cudaStream_t s, int64_t* launches);
+                             int64_t L, int64_t Kk, int heads, int hd, cudaStream_t s, int64_t* launches,
+                             const int32_t* rag = nullptr);
 // f3 (M, 3C): [gate_logit | local_t | global_t] -> out (M, C) = s*lt + (1-s)*gt, s = sigmoid(gate).
 cudaError_t launch_gate_mix(const float* f3, float* out, int64_t M, int C, cudaStream_t s, int64_t* launches);
 
@@ -127,7 +138,8 @@ cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, 
 cudaError_t launch_ctc_runs(const int32_t* pred, int32_t* tokens, int32_t* starts, int32_t* ends, int32_t* lens,
                             int64_t B, int64_t L, int blank, cudaStream_t s, int64_t* launches);
 cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
-                                int blank, int collapse, cudaStream_t s, int64_t* launches);
+                                int blank, int collapse, cudaStream_t s, int64_t* launches,
+                                const int32_t* rag = nullptr);
 
 // ---------------------------------------------------------------- CTC prefix beam search
 // per (utterance, frame) row: stats = (max, log sum exp(x - max)); top_tok (M, K) = the K best non-blank

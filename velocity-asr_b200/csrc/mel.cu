@@ -134,7 +134,7 @@ inline size_t mel_fft_smem(int n_mels) {
 __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
     const float* __restrict__ pcm, float* __restrict__ raw, double* __restrict__ part, int64_t S, int64_t T,
     int n_mels, const int* __restrict__ fb_lo, const int* __restrict__ fb_off, const float* __restrict__ fb_w,
-    const float* __restrict__ win, const float2* __restrict__ tw) {
+    const float* __restrict__ win, const float2* __restrict__ tw, const int32_t* __restrict__ rag) {
   extern __shared__ __align__(16) float mel_smem[];
   float2* s_tw = reinterpret_cast<float2*>(mel_smem);                  // NFFT float2
   float* s_win = mel_smem + 2 * NFFT;                                  // NFFT
@@ -145,14 +145,18 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * FPC;
-  const int nfr = (int)((T - t0) < FPC ? (T - t0) : FPC);     // frames of this CTA that exist
+  // ragged batch: this utterance has Sb <= S samples / Tb <= T frames; rows keep the strides of S and T
+  const int64_t Sb = rag ? rag[b * RAG_STRIDE + RAG_S] : S;
+  const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;
+  if (Tb <= t0) return;                                        // whole CTA past the utterance's end
+  const int nfr = (int)((Tb - t0) < FPC ? (Tb - t0) : FPC);   // frames of this CTA that exist
   const float* xb = pcm + b * S;
   const int nsamp = NHOP * (nfr - 1) + NFFT;
   for (int i = tid; i < nsamp; i += MEL_WARPS * 32) {
     int64_t g = t0 * NHOP + i - NPAD;           // index into the unpadded signal
     if (g < 0) g = -g;                          // reflect without repeating the edge sample (audio.py:100-101)
-    if (g >= S) g = 2 * (S - 1) - g;
-    s_x[i] = (g >= 0 && g < S) ? __ldg(xb + g) : 0.f;
+    if (g >= Sb) g = 2 * (Sb - 1) - g;
+    s_x[i] = (g >= 0 && g < Sb) ? __ldg(xb + g) : 0.f;
   }
   for (int i = tid; i < NFFT; i += MEL_WARPS * 32) {
     s_win[i] = __ldg(win + i);
@@ -231,12 +235,15 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
 __global__ void __launch_bounds__(MAX_MELS) mel_stats_combine_kernel(const double* __restrict__ part,
                                                                      float* __restrict__ mean,
                                                                      float* __restrict__ rstd, int64_t T,
-                                                                     int nblk, int n_mels) {
+                                                                     int nblk, int n_mels,
+                                                                     const int32_t* __restrict__ rag) {
   const int64_t b = blockIdx.x;
   const int j = threadIdx.x;
   if (j >= n_mels) return;
   double n = 0.0, mu = 0.0, m2 = 0.0;
-  for (int k = 0; k < nblk; ++k) {
+  if (rag) T = rag[b * RAG_STRIDE + RAG_T];        // the partials keep the row stride nblk of the longest
+  const int nb = (int)((T + FPC - 1) / FPC);
+  for (int k = 0; k < nb; ++k) {
     const double nk = (double)((T - (int64_t)k * FPC) < FPC ? (T - (int64_t)k * FPC) : FPC);
     const double* p = part + ((b * nblk + k) * n_mels + j) * 2;
     const double d = p[0] - mu;
@@ -291,15 +298,17 @@ __global__ void __launch_bounds__(1024) mel_stats_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict__ raw,
                                                          const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, float* __restrict__ out,
-                                                         int64_t T, int n_mels, int64_t fpu, int front) {
+                                                         int64_t T, int n_mels, int64_t fpu, int front,
+                                                         const int32_t* __restrict__ rag) {
   const int64_t b = blockIdx.y;
+  const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= fpu * n_mels) return;
   const int64_t p = idx / n_mels;
   const int j = (int)(idx - p * n_mels);
   const int64_t t = p - front;
   float v = 0.f;
-  if (t >= 0 && t < T) {
+  if (t >= 0 && t < Tb) {
     v = raw[(b * T + t) * n_mels + j];
     if (mean) v = (v - mean[b * n_mels + j]) * rstd[b * n_mels + j];
   }
@@ -332,7 +341,7 @@ int64_t mel_fft_blocks(int64_t T) { return (T + FPC - 1) / FPC; }
 
 cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B, int64_t S, int64_t T, int n_mels,
                            const int* fb_lo, const int* fb_off, const float* fb_w, const float* win,
-                           const float* tw, cudaStream_t s, int64_t* launches) {
+                           const float* tw, cudaStream_t s, int64_t* launches, const int32_t* rag) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   if (B > 65535 || n_mels > MAX_MELS || S <= NPAD) return cudaErrorInvalidValue;
   dim3 grid((unsigned)mel_fft_blocks(T), (unsigned)B);
@@ -340,16 +349,17 @@ cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B
   cudaError_t e = cudaFuncSetAttribute(mel_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   mel_fft_kernel<<<grid, MEL_WARPS * 32, smem, s>>>(pcm, raw, part, S, T, n_mels, fb_lo, fb_off, fb_w, win,
-                                                  reinterpret_cast<const float2*>(tw));
+                                                  reinterpret_cast<const float2*>(tw), rag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
 
 cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
-                                     cudaStream_t s, int64_t* launches) {
+                                     cudaStream_t s, int64_t* launches, const int32_t* rag) {
   if (B <= 0) return cudaSuccess;
   if (n_mels > MAX_MELS) return cudaErrorInvalidValue;
-  mel_stats_combine_kernel<<<(unsigned)B, MAX_MELS, 0, s>>>(part, mean, rstd, T, (int)mel_fft_blocks(T), n_mels);
+  mel_stats_combine_kernel<<<(unsigned)B, MAX_MELS, 0, s>>>(part, mean, rstd, T, (int)mel_fft_blocks(T), n_mels,
+                                                            rag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -367,11 +377,11 @@ cudaError_t launch_mel_stats(const float* raw, float* mean, float* rstd, int64_t
 
 cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* rstd, float* out, int64_t B,
                               int64_t T, int n_mels, int64_t frames_per_utt, int front, cudaStream_t s,
-                              int64_t* launches) {
+                              int64_t* launches, const int32_t* rag) {
   if (B <= 0) return cudaSuccess;
   if (B > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((frames_per_utt * n_mels + 255) / 256), (unsigned)B);
-  mel_finish_kernel<<<grid, 256, 0, s>>>(raw, mean, rstd, out, T, n_mels, frames_per_utt, front);
+  mel_finish_kernel<<<grid, 256, 0, s>>>(raw, mean, rstd, out, T, n_mels, frames_per_utt, front, rag);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

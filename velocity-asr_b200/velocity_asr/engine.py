@@ -23,6 +23,14 @@ def _token_lists(tokens: torch.Tensor, lens: torch.Tensor) -> List[List[int]]:
     return [tok[b, :n].tolist() for b, n in enumerate(lens.tolist())]
 
 
+def _lengths_tensor(lengths, B: int) -> torch.Tensor:
+    """Per-utterance lengths (list / tuple / tensor) -> contiguous host int32 tensor of B entries."""
+    t = torch.as_tensor(lengths).detach().to("cpu", torch.int32).contiguous().reshape(-1)
+    if t.numel() != B:
+        raise RuntimeError(f"expected {B} lengths, got {t.numel()}")
+    return t
+
+
 class _Engine:
     """Owns one vasr_handle (one GPU).  Re-uploads weights when the parameters change."""
 
@@ -127,9 +135,12 @@ class VELOCITYASR(nn.Module):
 
     # ---- reference API ----------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, mel_spectrogram: torch.Tensor, return_features: bool = False
+    def forward(self, mel_spectrogram: torch.Tensor, return_features: bool = False, lengths=None
                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, Dict[str, torch.Tensor]]]:
-        """(B, T, mel_bins) -> logits (B, (T+1)//2, vocab) [, features].  model.py:333-368"""
+        """(B, T, mel_bins) -> logits (B, (T+1)//2, vocab) [, features].  model.py:333-368.
+        `lengths` (B frame counts; not in the reference, whose collator pads and never masks): utterance b
+        has lengths[b] valid frames and its logits rows [: get_output_length(lengths[b])] equal those of
+        forward(mel[b:b+1, :lengths[b]]); rows past that are padding."""
         mel = self._check_input(mel_spectrogram, "mel_spectrogram")
         if mel.dim() != 3 or mel.size(2) != self.config.mel_bins:
             raise RuntimeError(f"expected (batch, frames, {self.config.mel_bins}) input, got {tuple(mel.shape)}")
@@ -137,6 +148,14 @@ class VELOCITYASR(nn.Module):
         B, T, _ = mel.shape
         L = self.get_output_length(T)
         logits = torch.empty(B, L, self.config.vocab_size, device=mel.device, dtype=torch.float32)
+        if lengths is not None:
+            if return_features:
+                raise NotImplementedError("return_features is not available together with lengths")
+            lens = _lengths_tensor(lengths, B)
+            if B > 0 and T > 0:
+                _native.check(eng.lib.vasr_forward_ragged(eng.handle, _native.ptr(mel), _native.ptr(lens), B, T,
+                                                          _native.ptr(logits), _stream_ptr(mel.device)))
+            return logits
         feats = None
         if return_features:
             feats = {k: torch.empty(B, L, self.config.d_model, device=mel.device, dtype=torch.float32)
@@ -154,30 +173,43 @@ class VELOCITYASR(nn.Module):
         return (input_length + 1) // 2
 
     @torch.no_grad()
-    def transcribe(self, audio: torch.Tensor) -> List[List[int]]:
+    def transcribe(self, audio: torch.Tensor, lengths=None) -> List[List[int]]:
         """Fused fast path: 16 kHz PCM (S,) | (B, S) -> greedy CTC token ids per utterance
         (compute_mel_spectrogram -> forward -> ctc_greedy_decode, scripts/transcribe.py:69-82).
         A CUDA tensor is consumed in place; a CPU tensor is copied host->device inside the call
-        (pin it for full PCIe speed) and only the token ids come back."""
+        (pin it for full PCIe speed) and only the token ids come back.
+        `lengths` (B sample counts): a ragged batch padded to S; utterance b is its first lengths[b] samples
+        and is transcribed exactly as transcribe(audio[b, :lengths[b]]) would (own reflect padding, mel
+        statistics, pooling windows, attention keys and decode length) in the same launches as its mates."""
         if audio.dim() == 1:
             audio = audio.unsqueeze(0)
         B, S = audio.shape
         dev = self._device()
         eng = self._engine(dev)
         L = self.get_output_length(1 + S // 160)
+        slen = None if lengths is None else _lengths_tensor(lengths, B)
         if audio.device.type == "cpu":
             pcm = audio.to(torch.float32).contiguous()
             tokens = torch.empty(B, L, dtype=torch.int32, pin_memory=True)
             lens = torch.empty(B, dtype=torch.int32, pin_memory=True)
-            _native.check(eng.lib.vasr_transcribe_host(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
-                                                       _native.ptr(lens)))
+            if slen is None:
+                _native.check(eng.lib.vasr_transcribe_host(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
+                                                           _native.ptr(lens)))
+            else:
+                _native.check(eng.lib.vasr_transcribe_ragged_host(eng.handle, _native.ptr(pcm), _native.ptr(slen), B, S,
+                                                                  _native.ptr(tokens), _native.ptr(lens)))
             return _token_lists(tokens, lens)
         else:
             pcm = self._check_input(audio, "audio")
             tokens = torch.empty(B, L, dtype=torch.int32, device=pcm.device)
             lens = torch.empty(B, dtype=torch.int32, device=pcm.device)
-            _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
-                                                  _native.ptr(lens), _stream_ptr(pcm.device)))
+            if slen is None:
+                _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
+                                                      _native.ptr(lens), _stream_ptr(pcm.device)))
+            else:
+                _native.check(eng.lib.vasr_transcribe_ragged(eng.handle, _native.ptr(pcm), _native.ptr(slen), B, S,
+                                                             _native.ptr(tokens), _native.ptr(lens),
+                                                             _stream_ptr(pcm.device)))
             tokens, lens = tokens.cpu(), lens.cpu()
         return _token_lists(tokens, lens)
 
@@ -187,7 +219,8 @@ class VELOCITYASR(nn.Module):
         batch i+1 is copied host->device on a second stream and the token ids of batch i-1 are copied
         back and turned into lists.  Yields one List[List[int]] per input batch, in order; results
         are identical to calling transcribe() on each batch.  Batches are (B, S) float32 CPU
-        tensors (pin them for full PCIe speed); shapes may change from batch to batch."""
+        tensors (pin them for full PCIe speed); shapes may change from batch to batch.  An item may also
+        be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths)."""
         dev = self._device()
         eng = self._engine(dev)
         comp = torch.cuda.current_stream(dev)
@@ -197,6 +230,9 @@ class VELOCITYASR(nn.Module):
         pending = None          # (slot, B) of the batch whose results are still on the device
         i = 0
         for audio in batches:
+            slen = None
+            if isinstance(audio, (tuple, list)):        # (padded batch, per-utterance sample counts): ragged
+                audio, slen = audio
             if audio.device.type != "cpu":
                 raise RuntimeError("transcribe_batches takes host batches; use transcribe() for CUDA tensors")
             if audio.dim() == 1:
@@ -217,8 +253,14 @@ class VELOCITYASR(nn.Module):
                 sl["pcm"].copy_(audio, non_blocking=True)
                 sl["h2d"].record(copy)
             comp.wait_event(sl["h2d"])
-            _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(sl["pcm"]), B, S, _native.ptr(sl["tok"]),
-                                                  _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
+            if slen is None:
+                _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(sl["pcm"]), B, S, _native.ptr(sl["tok"]),
+                                                      _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
+            else:
+                slen_t = _lengths_tensor(slen, B)       # stays referenced across the call (read synchronously)
+                _native.check(eng.lib.vasr_transcribe_ragged(
+                    eng.handle, _native.ptr(sl["pcm"]), _native.ptr(slen_t), B, S,
+                    _native.ptr(sl["tok"]), _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
             sl["free"].record(comp)
             sl["tok_h"].copy_(sl["tok"], non_blocking=True)
             sl["lens_h"].copy_(sl["lens"], non_blocking=True)
@@ -239,22 +281,23 @@ class VELOCITYASR(nn.Module):
     def transcribe_list(self, utterances: List[torch.Tensor], max_batch: int = 64) -> List[List[int]]:
         """Variable-length input: a list of 1-D PCM tensors -> token ids per utterance, in input order.
         The reference's collator pads with zeros and never masks (data.py:145-203), which makes an
-        utterance's result depend on its batch mates; here utterances of equal length are batched
-        together (at most `max_batch` per launch sequence) and nothing is padded, so every result equals
-        transcribe() of that utterance alone."""
+        utterance's result depend on its batch mates.  Here the utterances are sorted by length, cut into
+        batches of at most `max_batch`, padded to the longest of the batch and run as ragged batches
+        (transcribe(..., lengths=...)), so every result equals transcribe() of that utterance alone."""
         out: List[Optional[List[int]]] = [None] * len(utterances)
-        groups: Dict[int, List[int]] = {}
-        for i, u in enumerate(utterances):
+        for u in utterances:
             if u.dim() != 1:
                 raise RuntimeError("transcribe_list takes 1-D PCM tensors")
-            groups.setdefault(int(u.numel()), []).append(i)
+        order = sorted(range(len(utterances)), key=lambda i: int(utterances[i].numel()))
         dev = self._device()
-        for _, idx in sorted(groups.items()):
-            for j in range(0, len(idx), max_batch):
-                part = idx[j:j + max_batch]
-                batch = torch.stack([utterances[i].to(dev, torch.float32) for i in part])
-                for i, toks in zip(part, self.transcribe(batch)):
-                    out[i] = toks
+        for j in range(0, len(order), max_batch):
+            part = order[j:j + max_batch]
+            lens = [int(utterances[i].numel()) for i in part]
+            batch = torch.zeros(len(part), max(lens), device=dev, dtype=torch.float32)
+            for r, i in enumerate(part):
+                batch[r, :lens[r]] = utterances[i].to(dev, torch.float32)
+            for i, toks in zip(part, self.transcribe(batch, lengths=lens)):
+                out[i] = toks
         return out  # type: ignore[return-value]
 
     def extend_positional_table(self, rows: int) -> None:
