@@ -55,6 +55,37 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- activations with the reference's ATen semantics --------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// The same function for the projection epilogues, where erff's ~27 instructions per element made the GELU of a
+// tile cost as many issue slots as its MMAs:  gelu(x) = relu(x) - |x| * 0.5 erfc(|x| / sqrt 2), and
+// 0.5 erfc(a / sqrt 2) = 2^(a q(a) - 1) with q a degree-9 fit on [0, 6] (beyond 6 the term is < 6e-9 |x|).
+// Absolute error <= 2.4e-7 over [-12, 12] (half an ulp of the result at |x| ~ 4; the fp32 erf form has 4.5e-7).
+#define VASR_GELU_Q(F)                                                                                        \
+  F(1.037785637e-06f) F(-1.249625166e-05f) F(8.313555008e-05f) F(-2.954076626e-04f) F(1.900888492e-05f)       \
+  F(6.938213017e-03f) F(-5.244373530e-02f) F(-4.592177570e-01f) F(-1.151104808e+00f)
+__device__ __forceinline__ float gelu_poly(float x) {
+  const float a = fminf(fabsf(x), 6.0f);
+  float q = -3.721141795e-08f;
+#define VASR_STEP(c) q = fmaf(q, a, c);
+  VASR_GELU_Q(VASR_STEP)
+#undef VASR_STEP
+  const float e = ex2_approx(fmaf(q, a, -1.0f));
+  return fmaxf(x, 0.0f) - fabsf(x * e);
+}
+// two elements at a time: the Horner chain on the packed fp32x2 pipe
+__device__ __forceinline__ void gelu_poly2(float& x0, float& x1) {
+  const float a0 = fminf(fabsf(x0), 6.0f), a1 = fminf(fabsf(x1), 6.0f);
+  const u64 a = pack2(a0, a1);
+  u64 q = pack2(-3.721141795e-08f, -3.721141795e-08f);
+#define VASR_STEP(c) q = fma2(q, a, pack2(c, c));
+  VASR_GELU_Q(VASR_STEP)
+#undef VASR_STEP
+  q = fma2(q, a, pack2(-1.0f, -1.0f));
+  float p0, p1;
+  unpack2(q, p0, p1);
+  x0 = fmaxf(x0, 0.0f) - fabsf(x0 * ex2_approx(p0));
+  x1 = fmaxf(x1, 0.0f) - fabsf(x1 * ex2_approx(p1));
+}
+
 // F.softplus(beta=1, threshold=20) = x if x > 20 else log1p(exp(x)), evaluated as
 // max(x,0) + log1p(exp(-|x|)) with MUFU ex2/lg2 (series for tiny arguments): abs error ~1e-7.
 __device__ __forceinline__ float softplus_t20(float x) {

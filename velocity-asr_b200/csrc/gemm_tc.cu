@@ -192,7 +192,7 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 
 template <int ACT>
 __device__ __forceinline__ float apply_act_t(float v) {
-  if (ACT == ACT_GELU) return gelu_erf(v);
+  if (ACT == ACT_GELU) return gelu_poly(v);
   if (ACT == ACT_SOFTPLUS) return softplus_t20(v);
   if (ACT == ACT_SIGMOID) return sigmoid_f(v);
   return v;
@@ -364,8 +364,13 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
           x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
         }
         if (act_on) {
-          x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
-          x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+          if (ACT == ACT_GELU) {
+            gelu_poly2(x.x, x.y);
+            gelu_poly2(x.z, x.w);
+          } else {
+            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
+            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+          }
         }
         if (PE) {
           float4 p4 = pf4[j];
