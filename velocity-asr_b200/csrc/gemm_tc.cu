@@ -218,6 +218,9 @@ struct TcArgs {
   int prefetch;       // producer prefetches the next tile's A k-blocks into L2
   int dbg;            // debug (VASR_TC_DBG): 1 = epilogue skips its TMEM loads, 2 = skips staging + stores (garbage output)
   int rotate_n;       // rotate the n-tile index by the round number (see tile_coords)
+  int wres;           // pair kernel, W resident: pairs per n-tile (0 = off).  Each pair keeps ONE n-tile: its W k-blocks
+                      // are loaded once into the W halves of the stage ring (k-block kb always meets stage kb % nkb
+                      // because nkb divides the ring) and only A streams afterwards
   long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
 };
 // tile -> (m tile, n tile).  A persistent CTA takes tiles blockIdx.x, + gridDim.x, ...; with an n-tile
@@ -233,8 +236,15 @@ __device__ __forceinline__ void tile_coords(const TcArgs& g, int64_t tile64, int
   *mt = m;
   *nt = (int)((tile - m * n_tiles + (g.rotate_n ? m / per : 0u)) % n_tiles);
 }
+// the time stamps inside the MMA warp cost it 50-100 clocks each (CS2R + store), enough to change what they
+// measure; they are compiled in only with -DVASR_TC_TRACE_MMA
+#ifdef VASR_TC_TRACE_MMA
+#define MMA_TRACE(x) x
+#else
+#define MMA_TRACE(x)
+#endif
 constexpr int TRACE_SLOTS = 128;
-constexpr int TRACE_ROLES = 12;
+constexpr int TRACE_ROLES = 16;
 __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
 }
@@ -703,12 +713,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;   // pair tiles (256 rows)
   const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int64_t UNITS = npairs;
+  // tile walk of this pair: round-robin over all tiles, or (W resident) a fixed n-tile and every wres-th m-tile
+  int64_t first_tile = pair, tile_stride = npairs;
+  if (g.wres) {
+    const int64_t slot = pair / g.n_tiles, nt_own = pair % g.n_tiles;
+    first_tile = slot < g.wres ? slot * g.n_tiles + nt_own : total_tiles;
+    tile_stride = (int64_t)g.wres * g.n_tiles;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, cnt = 0;
     int tr_i = 0;
-    for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
+    for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       int nt;
       int64_t mt;
       tile_coords(g, tile, UNITS, &mt, &nt);
@@ -723,40 +740,53 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ++tr_i;
         const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
         const uint32_t wbar = mapa(BAR(PB_WFULL + stage), 0);
+        const bool load_w = !g.wres || cnt < (uint32_t)P_STAGES;      // W resident: first pass over the ring only
         if (elect_one()) {
           mbar_expect_tx(BAR(PB_AFULL + stage), TILE_BYTES);
           tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(PB_AFULL + stage));
-          if (leader) mbar_expect_tx(BAR(PB_WFULL + stage), 2 * TILE_BYTES);     // 4 x 8 KB from the two CTAs
-          tma_load_2d_pair(sb + TILE_BYTES, &tmWh, kb * TBK, wrow, wbar);
-          tma_load_2d_pair(sb + TILE_BYTES + TILE_BYTES / 2, &tmWl, kb * TBK, wrow, wbar);
+          if (load_w) {
+            if (leader) mbar_expect_tx(BAR(PB_WFULL + stage), 2 * TILE_BYTES);     // 4 x 8 KB from the two CTAs
+            tma_load_2d_pair(sb + TILE_BYTES, &tmWh, kb * TBK, wrow, wbar);
+            tma_load_2d_pair(sb + TILE_BYTES + TILE_BYTES / 2, &tmWl, kb * TBK, wrow, wbar);
+          }
         }
         __syncwarp();
+        ++cnt;
         if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // Measured (tools/gemm_trace.py, K = 192, N-tile 128): the k-blocks of a tile complete 1300 / 600 / 1050 /
+    // 790 / 800 / 790 clocks apart with the epilogue switched off (ideal 768 each: 12 MMAs x 64), i.e. ~800
+    // clocks are lost at the start of every tile, and the epilogue's staging + store phase costs the third and
+    // fourth k-block another ~1200.  Ruled out as the cause of the tile-start loss: an accumulator-switch
+    // penalty of the tensor pipe (tools/probes/mma_probe.cu: none), the epilogue's tcgen05.ld traffic
+    // (VASR_TC_DBG=3: same cadence), and this warp's own tile-boundary work (probing the barriers early and
+    // hoisting the tile arithmetic took ~400 clocks off its path and changed nothing).
     if (leader) {
       uint32_t stage = 0, phase = 0, cnt = 0;     // cnt: k-steps issued so far (TMEM A slot = cnt % P_ASLOTS)
-      int64_t it = 0;
+      uint32_t it = 0;
       int tr_i = 0;
-      for (int64_t tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+        MMA_TRACE(if (lane == 0) trace_ev(g, 10, (int)it);)
         int nt;
         int64_t mt_unused;
         tile_coords(g, tile, UNITS, &mt_unused, &nt);
-        int64_t nrem = g.N - (int64_t)nt * TBN;
+        const int64_t nrem = g.N - (int64_t)nt * TBN;
         const uint32_t n_mma = nrem >= TBN ? (uint32_t)TBN : (uint32_t)((nrem + 15) & ~15LL);
         // M = 256 across the pair
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((256u >> 4) << 24);
-        const uint32_t acc = (uint32_t)(it & 1);
-        mbar_wait_cluster(BAR(PB_TEMPTY + acc), (uint32_t)((it >> 1) & 1) ^ 1);
+        const uint32_t acc = it & 1u;
+        mbar_wait_cluster(BAR(PB_TEMPTY + acc), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        MMA_TRACE(if (lane == 0) trace_ev(g, 11, (int)it);)
         const uint32_t tmem_d = tmem_base + acc * TBN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_cluster(BAR(PB_WFULL + stage), phase);
+          if (!g.wres || cnt < (uint32_t)P_STAGES) mbar_wait_cluster(BAR(PB_WFULL + stage), phase);
           mbar_wait_cluster(BAR(PB_CONV + stage), phase);
           tc_fence_after();
-          if (lane == 0) trace_ev(g, 3, tr_i);
+          MMA_TRACE(if (lane == 0) trace_ev(g, 3, tr_i);)
           const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
           const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + TILE_BYTES + TILE_BYTES / 2);
           const uint32_t slot = cnt % P_ASLOTS;
@@ -772,7 +802,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma_commit_pair(BAR(PB_EMPTY + stage));
             umma_commit_pair(BAR(PB_AFREE + slot));
             if (kb == nkb - 1) umma_commit_pair(BAR(PB_TFULL + acc));
-            trace_ev(g, 4, tr_i);
+            MMA_TRACE(trace_ev(g, 4, tr_i);)
           }
           ++tr_i;
           ++cnt;
@@ -788,7 +818,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
     uint32_t stage = 0, phase = 0, cnt = 0;
     int tr_i = 0;
-    for (int64_t tile = pair; tile < total_tiles; tile += npairs) {
+    for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(PB_AFULL + stage), phase);
         if (threadIdx.x == 64) trace_ev(g, 1, tr_i);
@@ -821,7 +851,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
     epilogue_loop<ACT, PE, RESID, QUANT, true>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
-                                               (uint32_t)pair, (uint32_t)npairs, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
+                                               (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
                                                BAR(PB_TFULL), BAR(PB_TEMPTY));
   }
 
@@ -953,6 +983,17 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   if (tiles >= (1LL << 31) || rpb >= (1LL << 31)) return cudaErrorNotSupported;
   const int64_t units = pair ? num_sms / 2 : num_sms;
   const unsigned grid = (unsigned)((tiles < units ? tiles : units) * (pair ? 2 : 1));
+  // W resident (see TcArgs::wres): the k-blocks must tile the stage ring, every n-tile needs a pair, and each
+  // pair should see enough m-tiles to amortise its private copy of W.  VASR_TC_WRES=0 turns it off.
+  static const int wres_env = [] { const char* e = getenv("VASR_TC_WRES"); return e ? atoi(e) : 1; }();
+  a.wres = 0;
+  if (pair && wres_env) {
+    const int64_t nkb = (g.K + TBK - 1) / TBK, per = units / a.n_tiles, m_tiles = (int64_t)a.m_tiles_per_batch * nb;
+    if (nkb <= P_STAGES && P_STAGES % nkb == 0 && per >= 1 && m_tiles >= 4 * per && (int64_t)grid == 2 * units) {
+      a.wres = (int)per;
+      a.rotate_n = 0;
+    }
+  }
   const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;
   cudaError_t err = cudaSuccess;
   auto go1 = [&](auto kernel) {
