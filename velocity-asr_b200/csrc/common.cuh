@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libvasr is written for sm_100a (B200) only"
@@ -52,6 +53,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// Every kernel of the step is launched with programmatic stream serialisation (launch_k below): its CTAs may
+// become resident while the previous kernel is still running and park in pdl_wait() until that kernel has
+// completed and its writes are visible, so the ~1-2 us of launch latency between dependent kernels (104 per
+// step) and the projection kernel's prologue (barrier init, TMEM allocation, cluster sync) overlap the previous
+// kernel's tail.  Rules: pdl_trigger() first thing (lets the NEXT kernel's CTAs queue up as soon as all of
+// this one's have started); pdl_wait() before the first read of anything an earlier kernel wrote and before
+// the first global write; every kernel launched this way executes pdl_wait() (that is what makes "previous
+// kernel complete" imply "everything before it complete").  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- activations with the reference's ATen semantics --------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -117,6 +130,26 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case ACT_SIGMOID: return sigmoid_f(v);
     default: return v;
   }
+}
+
+// host: launch with the programmatic-serialisation attribute (VASR_PDL=0 turns it off)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VASR_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 }  // namespace vasr

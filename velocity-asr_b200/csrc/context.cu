@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) adaptive_pool_kernel(const float* __restr
                                                             float* __restrict__ out, int64_t L, int64_t K,
                                                             int C, const int32_t* __restrict__ rag, int f_in,
                                                             int f_out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = blockIdx.x, b = blockIdx.y;
   const int64_t Lb = rag ? rag[b * RAG_STRIDE + f_in] : L;      // rows keep the strides of L and K
   const int64_t Kb = rag ? rag[b * RAG_STRIDE + f_out] : K;
@@ -39,6 +41,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
                                                         const float* __restrict__ kv, float* __restrict__ o,
                                                         int64_t ldo, int64_t L, int64_t Kk, int heads, int hd,
                                                         const int32_t* __restrict__ rag) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float skv[];  // Kk x (2*A)
   const int A = heads * hd;
   const int64_t b = blockIdx.y;
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) gate_mix_kernel(const float* __restrict__ f3, float* __restrict__ out,
                                                        int64_t M, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= M * C) return;
   const int64_t m = idx / C;
@@ -161,9 +167,9 @@ cudaError_t launch_adaptive_pool(const float* x, int64_t ldx, float* out, int64_
   if (B <= 0 || K <= 0) return cudaSuccess;
   if (B > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)K, (unsigned)B);
-  adaptive_pool_kernel<<<grid, 256, 0, s>>>(x, ldx, out, L, K, C, rag, f_in, f_out);
+  const cudaError_t e = launch_k(adaptive_pool_kernel, grid, dim3(256), 0, s, x, ldx, out, L, K, C, rag, f_in, f_out);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_attention(const float* q, int64_t ldq, const float* kv, float* o, int64_t ldo, int64_t B,
@@ -174,16 +180,16 @@ cudaError_t launch_attention(const float* q, int64_t ldq, const float* kv, float
   const size_t smem = (size_t)Kk * 2 * heads * hd * sizeof(float);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((L + ATT_TOK - 1) / ATT_TOK), (unsigned)B);
-  attention_kernel<<<grid, heads * ATT_TOK, smem, s>>>(q, ldq, kv, o, ldo, L, Kk, heads, hd, rag);
+  const cudaError_t e = launch_k(attention_kernel, grid, dim3(heads * ATT_TOK), smem, s, q, ldq, kv, o, ldo, L, Kk, heads, hd, rag);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_gate_mix(const float* f3, float* out, int64_t M, int C, cudaStream_t s, int64_t* launches) {
   if (M <= 0) return cudaSuccess;
-  gate_mix_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, s>>>(f3, out, M, C);
+  const cudaError_t e = launch_k(gate_mix_kernel, dim3((unsigned)((M * C + 255) / 256)), dim3(256), 0, s, f3, out, M, C);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace vasr

@@ -12,6 +12,8 @@ namespace {
 // one warp per token row
 __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int32_t* __restrict__ pred,
                                                      int64_t M, int V) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(32) ctc_collapse_kernel(const int32_t* __restr
                                                           int32_t* __restrict__ tokens, int32_t* __restrict__ lens,
                                                           int64_t L, int blank, int collapse,
                                                           const int32_t* __restrict__ rag) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x;
   const int32_t* p = pred + b * L;
@@ -117,17 +121,17 @@ cudaError_t launch_ctc_runs(const int32_t* pred, int32_t* tokens, int32_t* start
 cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, cudaStream_t s,
                           int64_t* launches) {
   if (M <= 0) return cudaSuccess;
-  argmax_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(logits, pred, M, V);
+  const cudaError_t e = launch_k(argmax_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, s, logits, pred, M, V);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
                                 int blank, int collapse, cudaStream_t s, int64_t* launches, const int32_t* rag) {
   if (B <= 0) return cudaSuccess;
-  ctc_collapse_kernel<<<(unsigned)B, 32, 0, s>>>(pred, tokens, lens, L, blank, collapse, rag);
+  const cudaError_t e = launch_k(ctc_collapse_kernel, dim3((unsigned)B), dim3(32), 0, s, pred, tokens, lens, L, blank, collapse, rag);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace vasr

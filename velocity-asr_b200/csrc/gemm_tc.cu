@@ -216,7 +216,8 @@ struct TcArgs {
   const float* pe_freq;
   int pe_half;
   int prefetch;       // producer prefetches the next tile's A k-blocks into L2
-  int dbg;            // debug (VASR_TC_DBG): 1 = epilogue skips its TMEM loads, 2 = skips staging + stores (garbage output)
+  int dbg;            // debug (VASR_TC_DBG, garbage output): 1 = epilogue skips its TMEM loads, 2 = skips staging, math and
+                      // stores, 8 = skips the global stores only, 16 = skips the shared-memory transpose only
   int rotate_n;       // rotate the n-tile index by the round number (see tile_coords)
   int wres;           // pair kernel, W resident: pairs per n-tile (0 = off).  Each pair keeps ONE n-tile: its W k-blocks
                       // are loaded once into the W halves of the stage ring (k-block kb always meets stage kb % nkb
@@ -352,7 +353,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (c_begin + j >= c_end) break;
-      {
+      if (!(g.dbg & 16)) {
         uint8_t* srow = stg + lane * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -367,7 +368,8 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t rr = 4 * i + rsub;
-        float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(g.dbg & 16)) x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
         x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
         if (QUANT) {
           x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
@@ -389,7 +391,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
           x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
         }
         if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
-        if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
+        if (col_ok[j] && mi0 + rr < rpb && !(g.dbg & 8)) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
       }
       __syncwarp();               // the staging chunk is rewritten by the next chunk
       if (RESID && j == 0 && c_begin + 1 < c_end) load_resid(1);
@@ -402,6 +404,7 @@ template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from smem_raw (no integer round trip) so accesses compile to LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -437,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // TMEM address warp-uniform for the compiler (see elect_one)
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
+  pdl_wait();          // prologue done; global memory from here on (programmatic dependent launch, common.cuh)
 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
@@ -674,6 +678,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NBARS);
 
+  pdl_trigger();       // the next kernel's CTAs may queue up behind this one
+  if (threadIdx.x == 0) {   // descriptor fetches off the first TMA's critical path (kernel parameters: no dependency)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWl)) : "memory");
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -708,6 +718,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // TMEM address warp-uniform for the compiler (see elect_one)
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
+  // barriers, tensor memory and the cluster handshake are set up; from here on global memory is touched, which
+  // has to wait for the previous kernel (programmatic dependent launch, common.cuh)
+  pdl_wait();
 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;   // pair tiles (256 rows)
@@ -998,11 +1011,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   cudaError_t err = cudaSuccess;
   auto go1 = [&](auto kernel) {
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
+    if (err == cudaSuccess) err = launch_k(kernel, dim3(grid), dim3(TC_THREADS), SMEM_BYTES, s, tmA, tmWh, tmWl, a);
   };
   auto go2 = [&](auto kernel) {
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
-    if (err == cudaSuccess) kernel<<<grid, TC_THREADS, P_SMEM_BYTES, s>>>(tmA, tmWh, tmWl, a);
+    if (err == cudaSuccess) err = launch_k(kernel, dim3(grid), dim3(TC_THREADS), P_SMEM_BYTES, s, tmA, tmWh, tmWl, a);
   };
   const bool quant = g.q_scale != nullptr;
   if (quant) {   // config 5: the quantised modules are plain projections, or the temporal-binding conv (GELU + pos-enc)
@@ -1036,7 +1049,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
 #undef VASR_TC_CASE
   if (err != cudaSuccess) return err;
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 }  // namespace vasr

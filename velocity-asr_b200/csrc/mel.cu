@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
     const float* __restrict__ pcm, float* __restrict__ raw, double* __restrict__ part, int64_t S, int64_t T,
     int n_mels, const int* __restrict__ fb_lo, const int* __restrict__ fb_off, const float* __restrict__ fb_w,
     const float* __restrict__ win, const float2* __restrict__ tw, const int32_t* __restrict__ rag) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float mel_smem[];
   float2* s_tw = reinterpret_cast<float2*>(mel_smem);                  // NFFT float2
   float* s_win = mel_smem + 2 * NFFT;                                  // NFFT
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(MAX_MELS) mel_stats_combine_kernel(const doubl
                                                                      float* __restrict__ rstd, int64_t T,
                                                                      int nblk, int n_mels,
                                                                      const int32_t* __restrict__ rag) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t b = blockIdx.x;
   const int j = threadIdx.x;
   if (j >= n_mels) return;
@@ -300,6 +304,8 @@ __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict
                                                          const float* __restrict__ rstd, float* __restrict__ out,
                                                          int64_t T, int n_mels, int64_t fpu, int front,
                                                          const int32_t* __restrict__ rag) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t b = blockIdx.y;
   const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -348,20 +354,20 @@ cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B
   const size_t smem = mel_fft_smem(n_mels);
   cudaError_t e = cudaFuncSetAttribute(mel_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  mel_fft_kernel<<<grid, MEL_WARPS * 32, smem, s>>>(pcm, raw, part, S, T, n_mels, fb_lo, fb_off, fb_w, win,
-                                                  reinterpret_cast<const float2*>(tw), rag);
+  e = launch_k(mel_fft_kernel, grid, dim3(MEL_WARPS * 32), smem, s, pcm, raw, part, S, T, n_mels, fb_lo, fb_off, fb_w, win,
+               reinterpret_cast<const float2*>(tw), rag);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
                                      cudaStream_t s, int64_t* launches, const int32_t* rag) {
   if (B <= 0) return cudaSuccess;
   if (n_mels > MAX_MELS) return cudaErrorInvalidValue;
-  mel_stats_combine_kernel<<<(unsigned)B, MAX_MELS, 0, s>>>(part, mean, rstd, T, (int)mel_fft_blocks(T), n_mels,
-                                                            rag);
+  const cudaError_t e = launch_k(mel_stats_combine_kernel, dim3((unsigned)B), dim3(MAX_MELS), 0, s, part, mean, rstd, T,
+                                 (int)mel_fft_blocks(T), n_mels, rag);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_mel_stats(const float* raw, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
@@ -381,9 +387,10 @@ cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* 
   if (B <= 0) return cudaSuccess;
   if (B > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((frames_per_utt * n_mels + 255) / 256), (unsigned)B);
-  mel_finish_kernel<<<grid, 256, 0, s>>>(raw, mean, rstd, out, T, n_mels, frames_per_utt, front, rag);
+  const cudaError_t e = launch_k(mel_finish_kernel, grid, dim3(256), 0, s, raw, mean, rstd, out, T, n_mels, frames_per_utt,
+                                 front, rag);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace vasr

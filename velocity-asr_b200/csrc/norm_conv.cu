@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
                                                          float* __restrict__ y, int64_t ldy,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int64_t M, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(128) ln_dwconv_kernel(const float* __restrict_
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ bias, int64_t L, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int64_t b = blockIdx.y;
@@ -156,9 +160,10 @@ cudaError_t launch_layer_norm(const float* x, int64_t ldx, float* y, int64_t ldy
                               const float* beta, int64_t M, int C, cudaStream_t s, int64_t* launches) {
   if (M <= 0) return cudaSuccess;
   if (C > 32 * LN_MAX_PER_LANE) return cudaErrorInvalidValue;
-  layer_norm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, ldx, y, ldy, gamma, beta, M, C);
+  const cudaError_t e = launch_k(layer_norm_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, s, x, ldx, y, ldy, gamma,
+                                 beta, M, C);
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_ln_dwconv(const float* x, float* u, const float* gamma, const float* beta, const float* w,
@@ -168,14 +173,15 @@ cudaError_t launch_ln_dwconv(const float* x, float* u, const float* gamma, const
   if (C > 32 * DW_PER || k < 1 || k > MAXK || B > 65535) return cudaErrorInvalidValue;
   const int64_t runs = (L + RUN - 1) / RUN;
   dim3 grid((unsigned)((runs + 3) / 4), (unsigned)B);
+  cudaError_t e_launch = cudaSuccess;
   switch (k) {
-#define VASR_DW_CASE(KK) case KK: ln_dwconv_kernel<KK><<<grid, 128, 0, s>>>(x, u, gamma, beta, w, bias, L, C); break;
+#define VASR_DW_CASE(KK) case KK: e_launch = launch_k(ln_dwconv_kernel<KK>, grid, dim3(128), 0, s, x, u, gamma, beta, w, bias, L, C); break;
     VASR_DW_CASE(1) VASR_DW_CASE(2) VASR_DW_CASE(3) VASR_DW_CASE(4)
     VASR_DW_CASE(5) VASR_DW_CASE(6) VASR_DW_CASE(7) VASR_DW_CASE(8)
 #undef VASR_DW_CASE
   }
   if (launches) ++*launches;
-  return cudaGetLastError();
+  return e_launch;
 }
 
 }  // namespace vasr

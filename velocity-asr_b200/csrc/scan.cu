@@ -76,6 +76,8 @@ struct Anc {
 
 template <int LPR, bool STRUCT>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = LPR * SPL;
   constexpr int ROWS = SCAN_THREADS / LPR;
   constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : (LPR == 2 ? 1 : 0));
@@ -300,6 +302,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1, 2 or 3)
 __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int N = LPR * 16;
   constexpr int GROUPS = 32 / LPR;             // lane groups per warp
   constexpr int ROWS = WARPS * GROUPS * RPL;   // rows per CTA
@@ -644,11 +648,11 @@ cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
   auto go = [&](auto kernel) {
     if (SMEM > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    if (e == cudaSuccess) kernel<<<grid, WARPS * 32, SMEM, s>>>(a);
+    if (e == cudaSuccess) e = launch_k(kernel, grid, dim3(WARPS * 32), SMEM, s, a);
   };
   if (a.structured_a) go(scan_seq_kernel<LPR, WARPS, RPL, true>);
   else go(scan_seq_kernel<LPR, WARPS, RPL, false>);
-  return e != cudaSuccess ? e : cudaGetLastError();
+  return e;
 }
 
 // picks the CTA shape: rows per CTA must divide Di.  VASR_SCAN_RPL=1|2|3 overrides rows per lane.
@@ -688,9 +692,8 @@ cudaError_t launch_lpr(const ScanArgs& a, cudaStream_t s) {
   constexpr int ROWS = SCAN_THREADS / LPR8;
   if (a.Di % ROWS != 0) return cudaErrorInvalidValue;
   dim3 grid((unsigned)(a.Di / ROWS), (unsigned)a.B);
-  if (a.structured_a) scan_quirk_kernel<LPR8, true><<<grid, SCAN_THREADS, 0, s>>>(a);
-  else scan_quirk_kernel<LPR8, false><<<grid, SCAN_THREADS, 0, s>>>(a);
-  return cudaGetLastError();
+  if (a.structured_a) return launch_k(scan_quirk_kernel<LPR8, true>, grid, dim3(SCAN_THREADS), 0, s, a);
+  return launch_k(scan_quirk_kernel<LPR8, false>, grid, dim3(SCAN_THREADS), 0, s, a);
 }
 
 }  // namespace
