@@ -216,10 +216,9 @@ struct TcArgs {
   const float* pe_freq;
   int pe_half;
   int prefetch;       // producer prefetches the next tile's A k-blocks into L2
-  int dbg;            // debug (VASR_TC_DBG, garbage output): 1 = epilogue skips its TMEM loads, 2 = skips staging, math and
-                      // stores, 8 = skips the global stores only, 16 = skips the shared-memory transpose only
+  int dbg;            // debug (VASR_TC_DBG, garbage output): 1 = epilogue skips its TMEM loads, 2 = skips staging, math and stores
   int rotate_n;       // rotate the n-tile index by the round number (see tile_coords)
-  int wres;           // pair kernel, W resident: pairs per n-tile (0 = off).  Each pair keeps ONE n-tile: its W k-blocks
+  int wres;           // pair kernel instantiated with WRES: pairs per n-tile.  Each pair keeps ONE n-tile: its W k-blocks
                       // are loaded once into the W halves of the stage ring (k-block kb always meets stage kb % nkb
                       // because nkb divides the ring) and only A streams afterwards
   long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
@@ -353,7 +352,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (c_begin + j >= c_end) break;
-      if (!(g.dbg & 16)) {
+      {
         uint8_t* srow = stg + lane * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -368,8 +367,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t rr = 4 * i + rsub;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!(g.dbg & 16)) x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
         x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
         if (QUANT) {
           x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
@@ -391,7 +389,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
           x.x += p4.x; x.y += p4.y; x.z += p4.z; x.w += p4.w;
         }
         if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
-        if (col_ok[j] && mi0 + rr < rpb && !(g.dbg & 8)) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
+        if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
       }
       __syncwarp();               // the staging chunk is rewritten by the next chunk
       if (RESID && j == 0 && c_begin + 1 < c_end) load_resid(1);
@@ -669,7 +667,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int ACT, bool PE, bool RESID, bool QUANT>
+template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                 const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
@@ -728,7 +726,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int64_t UNITS = npairs;
   // tile walk of this pair: round-robin over all tiles, or (W resident) a fixed n-tile and every wres-th m-tile
   int64_t first_tile = pair, tile_stride = npairs;
-  if (g.wres) {
+  if (WRES) {
     const int64_t slot = pair / g.n_tiles, nt_own = pair % g.n_tiles;
     first_tile = slot < g.wres ? slot * g.n_tiles + nt_own : total_tiles;
     tile_stride = (int64_t)g.wres * g.n_tiles;
@@ -753,7 +751,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ++tr_i;
         const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
         const uint32_t wbar = mapa(BAR(PB_WFULL + stage), 0);
-        const bool load_w = !g.wres || cnt < (uint32_t)P_STAGES;      // W resident: first pass over the ring only
+        const bool load_w = !WRES || cnt < (uint32_t)P_STAGES;        // W resident: first pass over the ring only
         if (elect_one()) {
           mbar_expect_tx(BAR(PB_AFULL + stage), TILE_BYTES);
           tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(PB_AFULL + stage));
@@ -795,8 +793,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         MMA_TRACE(if (lane == 0) trace_ev(g, 11, (int)it);)
         const uint32_t tmem_d = tmem_base + acc * TBN;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
-          if (!g.wres || cnt < (uint32_t)P_STAGES) mbar_wait_cluster(BAR(PB_WFULL + stage), phase);
+          if (!WRES || cnt < (uint32_t)P_STAGES) mbar_wait_cluster(BAR(PB_WFULL + stage), phase);
           mbar_wait_cluster(BAR(PB_CONV + stage), phase);
           tc_fence_after();
           MMA_TRACE(if (lane == 0) trace_ev(g, 3, tr_i);)
@@ -1004,10 +1003,12 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
     const int64_t nkb = (g.K + TBK - 1) / TBK, per = units / a.n_tiles, m_tiles = (int64_t)a.m_tiles_per_batch * nb;
     if (nkb <= P_STAGES && P_STAGES % nkb == 0 && per >= 1 && m_tiles >= 4 * per && (int64_t)grid == 2 * units) {
       a.wres = (int)per;
-      a.rotate_n = 0;
     }
   }
   const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;
+  // W-resident instantiations exist for the plain and the GELU projection only (in_proj, ffn1, CTC head, q / k / v)
+  if (pe || rs || g.q_scale || !(g.act == ACT_NONE || g.act == ACT_GELU)) a.wres = 0;
+  if (a.wres) a.rotate_n = 0;
   cudaError_t err = cudaSuccess;
   auto go1 = [&](auto kernel) {
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -1034,6 +1035,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
       if (pe && rs) go2(gemm_tc2_kernel<ACTV, true, true, false>);                           \
       else if (pe) go2(gemm_tc2_kernel<ACTV, true, false, false>);                           \
       else if (rs) go2(gemm_tc2_kernel<ACTV, false, true, false>);                           \
+      else if (a.wres && ACTV == ACT_NONE) go2(gemm_tc2_kernel<ACT_NONE, false, false, false, true>);   \
+      else if (a.wres && ACTV == ACT_GELU) go2(gemm_tc2_kernel<ACT_GELU, false, false, false, true>);   \
       else go2(gemm_tc2_kernel<ACTV, false, false, false>);                                  \
     } else {                                                                                 \
       if (pe && rs) go1(gemm_tc_kernel<ACTV, true, true, false>);                            \
