@@ -33,7 +33,10 @@ def run(B=64, L=751, Di=384, N=64, mode="sequential", structured=True, gate=True
 
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
-    cases = [dict()] if quick else [dict(), dict(structured=False), dict(mode="parallel"), dict(N=32, L=93),
+    if "--quirk" in sys.argv:
+        cases = [dict(mode="parallel", N=32, L=93), dict(mode="parallel")]
+    else:
+      cases = [dict()] if quick else [dict(), dict(structured=False), dict(mode="parallel"), dict(N=32, L=93),
                                     dict(B=16, L=30001, iters=5), dict(B=512, iters=5), dict(B=1, L=501)]
     for c in cases:
         print(json.dumps(run(**c)), flush=True)

@@ -112,7 +112,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   a1 = a2 = a3 = cur;
   float hi_hp[HL][SPL], hi_H[HL][SPL];
   double hi_S[HL];
-  for (int l = 0; l < HL; ++l) {
+  // only the levels an index below L can reach are ever read (index 8q with z trailing zeros reads level
+  // z + 1 = entry z - 3, and 2^z < L).  These arrays are indexed dynamically, i.e. they live in local memory;
+  // clearing all 22 of them cost a short sequence — the global branch runs L = 93 — more than its 93 steps.
+  int hl_used = 0;
+  while (hl_used < HL && (1LL << (hl_used + 3)) < a.L) ++hl_used;
+  for (int l = 0; l < hl_used; ++l) {
     hi_S[l] = 0.0;
 #pragma unroll
     for (int k = 0; k < SPL; ++k) hi_hp[l][k] = hi_H[l][k] = 0.f;
