@@ -371,7 +371,7 @@ def run_own_arm(args):
                          "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the
                          # ncu --set full capture summarised in profiles/r01_ncu_full_summary.md
-                         "traffic": 303339520 if (B, L, di, cfg.ssm_state_dim) == (64, 751, 384, 64) else None,
+                         "traffic": 303103232 if (B, L, di, cfg.ssm_state_dim) == (64, 751, 384, 64) else None,
                          "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": local_ms,
                          "scan_launches_per_step": n_scan, "scan_ms_per_step": scan_total_ms,
                          "scan_share_of_step": scan_total_ms / step_total_ms,
