@@ -5,6 +5,8 @@ numpy oracle on fresh seeded inputs, (3) size-independent properties at BASELINE
 Tolerances (BASELINE.json north_star): mel 1e-4 absolute; activations / logits 1e-3 relative
 to the tensor's max magnitude (fp32 path: observed ~1e-5); token ids bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -13,6 +15,7 @@ import fixtures_util as FU
 import velocity_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 LOGIT_RTOL = 1e-3
 MEL_ATOL = 1e-4
@@ -369,6 +372,28 @@ def test_ragged_batch_equals_each_utterance_alone(va, mode):
         m.transcribe(pcm.cuda(), lengths=[S + 1] + lens[1:])
     with pytest.raises(RuntimeError):
         m.transcribe(pcm.cuda(), lengths=lens[1:])
+
+
+def test_programmatic_launch_is_a_pure_scheduling_change(va):
+    """The kernels of the step are launched with programmatic stream serialisation (common.cuh): the same
+    forward in a fresh process with VASR_PDL=0 (plain stream order) must give bit-identical logits."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import fixtures_util as FU, velocity_asr as va\n"
+        "torch.manual_seed(FU.WEIGHT_SEED)\n"
+        "m = va.VELOCITYASR(va.VelocityASRConfig(scan_mode='sequential')).cuda().eval()\n"
+        "out = m(va.compute_mel_spectrogram(FU.synth_audio(3, 24000).cuda()))\n"
+        "print(hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest())\n"
+    ) % (os.path.join(ROOT, "velocity-asr_b200"), os.path.join(ROOT, "tests"))
+    digests = []
+    for pdl in ("0", "1"):
+        env = dict(os.environ, VASR_PDL=pdl)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
 
 
 def test_long_form_needs_longer_table(va):
