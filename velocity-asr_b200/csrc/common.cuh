@@ -59,8 +59,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 // become resident while the previous kernel is still running and park in pdl_wait() until that kernel has
 // completed and its writes are visible, so the ~1-2 us of launch latency between dependent kernels (104 per
 // step) and the projection kernel's prologue (barrier init, TMEM allocation, cluster sync) overlap the previous
-// kernel's tail.  Rules: pdl_trigger() first thing (lets the NEXT kernel's CTAs queue up as soon as all of
-// this one's have started); pdl_wait() before the first read of anything an earlier kernel wrote and before
+// kernel's tail.  Rules: pdl_trigger() lets the NEXT kernel's CTAs queue up once every CTA of this one has
+// called it or exited — first thing in the short multi-wave kernels, but only near the END of the single-wave
+// kernels that run long (scan: before its last block; projections: at a CTA's last tile), because CTAs parked
+// in griddepcontrol.wait next to a running kernel slow it down; pdl_wait() before the first read of anything an
+// earlier kernel wrote and before
 // the first global write; every kernel launched this way executes pdl_wait() (that is what makes "previous
 // kernel complete" imply "everything before it complete").  Without the launch attribute both are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }

@@ -286,6 +286,10 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
   const uint32_t rpb = (uint32_t)g.rows_per_batch;
   uint32_t it = 0;
   for (uint32_t tile = first_tile; tile < total_tiles32; tile += tile_stride, ++it) {
+    // last tile of this CTA: the next kernel may be launched (programmatic dependent launch, common.cuh).  Not
+    // earlier: a persistent grid that let its successor's CTAs sit resident in griddepcontrol.wait for its whole
+    // run time would pay for it (see scan_seq_kernel).
+    if (tile + tile_stride >= total_tiles32) pdl_trigger();
     const uint32_t mt = tile / n_tiles;
     const uint32_t nt = (tile % n_tiles + (g.rotate_n ? mt / per : 0u)) % n_tiles;
     const uint32_t batch = mt / mtpb;
@@ -402,7 +406,6 @@ template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
-  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   // keep the pointer derived from smem_raw (no integer round trip) so accesses compile to LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -676,7 +679,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NBARS);
 
-  pdl_trigger();       // the next kernel's CTAs may queue up behind this one
   if (threadIdx.x == 0) {   // descriptor fetches off the first TMA's critical path (kernel parameters: no dependency)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWh)) : "memory");

@@ -76,7 +76,6 @@ struct Anc {
 
 template <int LPR, bool STRUCT>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
-  pdl_trigger();
   pdl_wait();
   constexpr int N = LPR * SPL;
   constexpr int ROWS = SCAN_THREADS / LPR;
@@ -124,6 +123,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   }
 
   for (int64_t tc0 = 0; tc0 < L; tc0 += TCQ) {
+    if (tc0 + TCQ >= L) pdl_trigger();     // last chunk: see scan_seq_kernel
     const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
     for (int idx = tid; idx < TCQ * (N / 4); idx += SCAN_THREADS) {
       const int t = idx / (N / 4), f = idx % (N / 4);
@@ -307,7 +307,6 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1, 2 or 3)
 __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
-  pdl_trigger();
   pdl_wait();
   constexpr int N = LPR * 16;
   constexpr int GROUPS = 32 / LPR;             // lane groups per warp
@@ -641,6 +640,11 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 :
       fvalid = tcn - s0;
     }
   }
+  // Programmatic launch of the next kernel only now: this grid is a single wave that runs for the whole
+  // sequence (milliseconds at 600 s utterances), and CTAs of the next kernel that sit resident in
+  // griddepcontrol.wait all that time cost this issue-bound kernel dearly (config 4: 124 ms per batch with the
+  // trigger at the top of the kernel, 79 ms without programmatic launch at all).
+  pdl_trigger();
   finalize();
 }
 
