@@ -117,6 +117,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on the first
+# communicator), so file descriptor 1 points at stderr while the benchmark runs and is restored for the line.
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- reference ---
 def load_reference_impl():
     """(kind, module): the unmodified reference if it travelled with the repo, else None."""
@@ -218,7 +238,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- own arm ----
@@ -385,7 +405,7 @@ def run_own_arm(args):
             except Exception as exc:  # the baseline must never sink the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc!r}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,6 +424,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
