@@ -402,6 +402,112 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
   }
 }
 
+// Epilogue of the 192-column pair kernel (plain projections, optional residual): six 32-column chunks per tile,
+// three per warp.  Two chunks are read at once as above; the first is transposed and stored, then its registers
+// take the third chunk and only then is the accumulator handed back (the tile's MMAs take 13.8 k clocks, the
+// epilogue has time).  Same staging, same coalesced 128-byte row segments as epilogue_loop.
+template <bool RESID>
+__device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
+                                                 uint32_t tile_stride, uint32_t total_tiles32, uint32_t rank,
+                                                 uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
+  constexpr uint32_t tmem_base = 0u;
+  constexpr uint32_t TN = 192, TM = 2 * TBM;
+  auto arrive_empty = [&](uint32_t acc) {
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t r;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar_tempty0_local + 8u * acc), "r"(0u));
+      asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+    }
+  };
+  const int q = warp & 3;
+  const int chalf = (warp - 6) >> 2;              // which three of the six 32-column chunks
+  const int cc = lane & 7, rsub = lane >> 3;
+  const uint32_t n_tiles = (uint32_t)g.n_tiles, mtpb = (uint32_t)g.m_tiles_per_batch;
+  const uint32_t rpb = (uint32_t)g.rows_per_batch;
+  uint32_t it = 0;
+  for (uint32_t tile = first_tile; tile < total_tiles32; tile += tile_stride, ++it) {
+    if (tile + tile_stride >= total_tiles32) pdl_trigger();        // last tile of this CTA (see epilogue_loop)
+    const uint32_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+    const uint32_t batch = mt / mtpb;
+    const uint32_t mi0 = (mt % mtpb) * TM + rank * TBM + q * 32;
+    const uint32_t ncol0 = nt * TN;
+    const uint32_t nrem = (uint32_t)g.N - ncol0;
+    const int nchunks = nrem >= TN ? 6 : (int)((nrem + 31) >> 5);
+    const uint32_t acc = it & 1u;
+    const int c_begin = 3 * chalf, c_end = (c_begin + 3 < nchunks) ? c_begin + 3 : nchunks;
+    const uint32_t n0 = ncol0 + c_begin * 32 + 4 * cc;
+    const int64_t mrow0 = (int64_t)batch * rpb + mi0;
+    float* crow = g.C + mrow0 * g.ldc + n0;
+    const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
+    float4 b4[3];
+    bool col_ok[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t n = n0 + 32 * j;
+      col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;
+      b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+    }
+    float4 r4[8];
+    auto load_resid = [&](int j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = 4 * i + rsub;
+        r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RESID && col_ok[j] && mi0 + rr < rpb)
+          r4[i] = __ldg(reinterpret_cast<const float4*>(rrow + (int64_t)rr * g.ldr + 32 * j));
+      }
+    };
+    if (RESID) load_resid(0);
+    mbar_wait(bar_tfull0 + 8u * acc, (it >> 1) & 1u);
+    tc_fence_after();
+    if (c_begin >= c_end) {
+      tc_fence_before();
+      arrive_empty(acc);
+      continue;
+    }
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c_begin * 32;
+    tmem_ld32_issue(taddr, v0);
+    if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+    tmem_ld_wait();
+    // chunk j of this warp: registers -> swizzled staging -> 128-byte row segments (+ bias, residual) -> global
+    auto emit = [&](const uint32_t (&v)[32], int j) {
+      uint8_t* srow = stg + lane * 128;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = 4 * i + rsub;
+        float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
+        if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
+      }
+      __syncwarp();
+    };
+    emit(v0, 0);
+    const bool has2 = c_begin + 2 < c_end;
+    if (has2) {
+      tmem_ld32_issue(taddr + 64, v0);
+      tmem_ld_wait();
+    }
+    tc_fence_before();
+    arrive_empty(acc);                  // everything this warp needs of the accumulator is in registers
+    if (c_begin + 1 < c_end) {
+      if (RESID) load_resid(1);
+      emit(v1, 1);
+    }
+    if (has2) {
+      if (RESID) load_resid(2);
+      emit(v0, 2);
+    }
+  }
+}
+
 template <int ACT, bool PE, bool RESID, bool QUANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
@@ -609,6 +715,27 @@ constexpr int PB_AFULL = 0, PB_WFULL = P_STAGES, PB_CONV = 2 * P_STAGES, PB_EMPT
               PB_TFULL = 4 * P_STAGES, PB_TEMPTY = 4 * P_STAGES + 2, PB_AFREE = 4 * P_STAGES + 4;
 constexpr int P_NBARS = 4 * P_STAGES + 4 + P_ASLOTS;
 
+// The same kernel with 192-column tiles (TN = 192), for N = 192 / 576: with 128-column tiles those projections end
+// in a 64-column tile whose k-blocks complete at the pace of the control path (converter and MMA warps, ~770
+// clocks) although their MMAs take 384 — half the tile time at half the tensor rate, and A loaded and converted
+// twice per row block.  One 192-column MMA per k-step (96 clocks) is tensor-bound again.  Costs: 2 x 192
+// accumulator columns leave room for two A slots only, and a stage grows to 40 KB (four of them).
+template <int TN>
+struct PairCfg {
+  static constexpr int W_HALF_BYTES = (TN / 2) * TBK * 4;              // one CTA's rows of W_hi (or W_lo) of a stage
+  static constexpr int STAGE_BYTES = TILE_BYTES + 2 * W_HALF_BYTES;     // A | W_hi half | W_lo half
+  static constexpr int STAGES = TN == 128 ? 6 : 4;
+  static constexpr int ASLOTS = TN == 128 ? 4 : 2;
+  static constexpr uint32_t A0 = 2 * TN;                               // first A column (two accumulators before it)
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 512 + 1024;
+  static constexpr int AFULL = 0, WFULL = STAGES, CONV = 2 * STAGES, EMPTY = 3 * STAGES, TFULL = 4 * STAGES,
+                       TEMPTY = 4 * STAGES + 2, AFREE = 4 * STAGES + 4, NBARS = 4 * STAGES + 4 + ASLOTS;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+  static_assert(A0 + ASLOTS * 64 <= 512, "tensor memory");
+};
+static_assert(PairCfg<128>::STAGE_BYTES == P_STAGE_BYTES && PairCfg<128>::SMEM_BYTES == P_SMEM_BYTES, "TN = 128 is the layout above");
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -670,10 +797,20 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false>
+template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false, int TN = 128>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                 const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
+  // the tile-width dependent layout, under the names the body uses (they shadow the TN = 128 globals)
+  using Cfg = PairCfg<TN>;
+  constexpr int TBN = TN;
+  constexpr int P_STAGE_BYTES = Cfg::STAGE_BYTES, P_STAGES = Cfg::STAGES, P_ASLOTS = Cfg::ASLOTS;
+  constexpr int P_BAR_OFFSET = Cfg::BAR_OFFSET, P_NBARS = Cfg::NBARS;
+  constexpr int PB_AFULL = Cfg::AFULL, PB_WFULL = Cfg::WFULL, PB_CONV = Cfg::CONV, PB_EMPTY = Cfg::EMPTY,
+                PB_TFULL = Cfg::TFULL, PB_TEMPTY = Cfg::TEMPTY, PB_AFREE = Cfg::AFREE;
+  constexpr uint32_t TMEM_A0 = Cfg::A0;
+  constexpr int W_HALF_BYTES = Cfg::W_HALF_BYTES;
+  static_assert(!(WRES && TN != 128), "the W-resident schedule exists for 128-column tiles only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
@@ -758,9 +895,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_expect_tx(BAR(PB_AFULL + stage), TILE_BYTES);
           tma_load_3d(sb, &tmA, kb * TBK, mi0, batch, BAR(PB_AFULL + stage));
           if (load_w) {
-            if (leader) mbar_expect_tx(BAR(PB_WFULL + stage), 2 * TILE_BYTES);     // 4 x 8 KB from the two CTAs
+            if (leader) mbar_expect_tx(BAR(PB_WFULL + stage), 4 * W_HALF_BYTES);   // hi and lo halves from the two CTAs
             tma_load_2d_pair(sb + TILE_BYTES, &tmWh, kb * TBK, wrow, wbar);
-            tma_load_2d_pair(sb + TILE_BYTES + TILE_BYTES / 2, &tmWl, kb * TBK, wrow, wbar);
+            tma_load_2d_pair(sb + TILE_BYTES + W_HALF_BYTES, &tmWl, kb * TBK, wrow, wbar);
           }
         }
         __syncwarp();
@@ -802,7 +939,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           MMA_TRACE(if (lane == 0) trace_ev(g, 3, tr_i);)
           const uint32_t sb = stage0 + stage * P_STAGE_BYTES;
-          const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + TILE_BYTES + TILE_BYTES / 2);
+          const uint64_t db_hi = umma_desc(sb + TILE_BYTES), db_lo = umma_desc(sb + TILE_BYTES + W_HALF_BYTES);
           const uint32_t slot = cnt % P_ASLOTS;
           const uint32_t a_hi = tmem_base + TMEM_A0 + slot * 64, a_lo = a_hi + 32;
           if (elect_one()) {
@@ -864,9 +1001,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
-    epilogue_loop<ACT, PE, RESID, QUANT, true>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
-                                               (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
-                                               BAR(PB_TFULL), BAR(PB_TEMPTY));
+    if constexpr (TN == 192) {
+      static_assert(TN != 192 || (ACT == ACT_NONE && !PE && !QUANT), "192-column tiles: plain projections only");
+      epilogue_loop192<RESID>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+                              (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, rank, BAR(PB_TFULL),
+                              BAR(PB_TEMPTY));
+    } else {
+      epilogue_loop<ACT, PE, RESID, QUANT, true>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+                                                 (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
+                                                 BAR(PB_TFULL), BAR(PB_TEMPTY));
+    }
   }
 
   tc_fence_before();
@@ -961,6 +1105,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   // VASR_GEMM=tc1 selects the single-CTA kernel
   static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return !(e && strcmp(e, "tc1") == 0); }();
   const bool pair = use_pair && num_sms >= 2;
+  // 192-column tiles (PairCfg<192>) where 128-column ones would end in a 64-column tile: N = 192, 576, ...;
+  // plain projections (optional residual) only.  VASR_TC_T192=0 turns it off.
+  static const int t192_env = [] { const char* e = getenv("VASR_TC_T192"); return e ? atoi(e) : 1; }();
+  const bool t192 = pair && t192_env && g.N % 192 == 0 && g.N % TBN != 0 && g.act == ACT_NONE && !g.pe_time && !g.q_scale;
+  const int tn = t192 ? 192 : TBN;
   CUtensorMap tmA, tmWh, tmWl;
   {
     const uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)rpb, (uint64_t)nb};
@@ -971,7 +1120,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t str[1] = {(uint64_t)g.K * 4};
-    const uint32_t box[2] = {TBK, (uint32_t)(pair ? TBN / 2 : TBN)};     // a CTA of a pair loads half of the W tile
+    const uint32_t box[2] = {TBK, (uint32_t)(pair ? tn / 2 : tn)};       // a CTA of a pair loads half of the W tile
     if (!make_map(&tmWh, g.W_split, 2, dims, str, box)) return cudaErrorNotSupported;
     if (!make_map(&tmWl, g.W_split + g.N * g.K, 2, dims, str, box)) return cudaErrorNotSupported;
   }
@@ -980,7 +1129,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.rows_per_batch = rpb;
   a.n_batches = nb;
   a.m_tiles_per_batch = (int)((rpb + (pair ? 2 : 1) * TBM - 1) / ((pair ? 2 : 1) * TBM));
-  a.n_tiles = (int)((g.N + TBN - 1) / TBN);
+  a.n_tiles = (int)((g.N + tn - 1) / tn);
   a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act_from = g.act_from;
   a.q_scale = g.q_scale; a.q_zp = g.q_zp;
   a.resid = g.resid; a.ldr = g.ldr;
@@ -1009,7 +1158,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   }
   const bool pe = g.pe_time != nullptr, rs = g.resid != nullptr;
   // W-resident instantiations exist for the plain and the GELU projection only (in_proj, ffn1, CTC head, q / k / v)
-  if (pe || rs || g.q_scale || !(g.act == ACT_NONE || g.act == ACT_GELU)) a.wres = 0;
+  if (pe || rs || g.q_scale || !(g.act == ACT_NONE || g.act == ACT_GELU) || t192) a.wres = 0;
   if (a.wres) a.rotate_n = 0;
   cudaError_t err = cudaSuccess;
   auto go1 = [&](auto kernel) {
@@ -1020,6 +1169,19 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (err == cudaSuccess) err = launch_k(kernel, dim3(grid), dim3(TC_THREADS), P_SMEM_BYTES, s, tmA, tmWh, tmWl, a);
   };
+  auto go192 = [&](auto kernel) {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<192>::SMEM_BYTES);
+    if (err == cudaSuccess)
+      err = launch_k(kernel, dim3(grid), dim3(TC_THREADS), PairCfg<192>::SMEM_BYTES, s, tmA, tmWh, tmWl, a);
+  };
+  if (t192) {
+    a.rotate_n = 0;
+    if (rs) go192(gemm_tc2_kernel<ACT_NONE, false, true, false, false, 192>);
+    else go192(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 192>);
+    if (err != cudaSuccess) return err;
+    if (launches) ++*launches;
+    return cudaSuccess;
+  }
   const bool quant = g.q_scale != nullptr;
   if (quant) {   // config 5: the quantised modules are plain projections, or the temporal-binding conv (GELU + pos-enc)
     if (rs || !((g.act == ACT_NONE && !pe) || (g.act == ACT_GELU && pe))) return cudaErrorNotSupported;
