@@ -406,7 +406,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 // three per warp.  Two chunks are read at once as above; the first is transposed and stored, then its registers
 // take the third chunk and only then is the accumulator handed back (the tile's MMAs take 13.8 k clocks, the
 // epilogue has time).  Same staging, same coalesced 128-byte row segments as epilogue_loop.
-template <bool RESID>
+template <int ACT, bool RESID>
 __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
                                                  uint32_t tile_stride, uint32_t total_tiles32, uint32_t rank,
                                                  uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
@@ -484,6 +484,15 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
         const uint32_t rr = 4 * i + rsub;
         float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
         x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        if (ACT != ACT_NONE && n0 + 32 * j >= (uint32_t)g.act_from) {
+          if (ACT == ACT_GELU) {
+            gelu_poly2(x.x, x.y);
+            gelu_poly2(x.z, x.w);
+          } else {
+            x.x = apply_act_t<ACT>(x.x); x.y = apply_act_t<ACT>(x.y);
+            x.z = apply_act_t<ACT>(x.z); x.w = apply_act_t<ACT>(x.w);
+          }
+        }
         if (RESID) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
         if (col_ok[j] && mi0 + rr < rpb) *reinterpret_cast<float4*>(crow + (int64_t)rr * g.ldc + 32 * j) = x;
       }
@@ -1002,8 +1011,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
     if constexpr (TN == 192) {
-      static_assert(TN != 192 || (ACT == ACT_NONE && !PE && !QUANT), "192-column tiles: plain projections only");
-      epilogue_loop192<RESID>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+      static_assert(TN != 192 || (ACT != ACT_SIGMOID && !PE && !QUANT), "192-column tiles: no pos-enc / quantised / sigmoid epilogue");
+      epilogue_loop192<ACT, RESID>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
                               (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, rank, BAR(PB_TFULL),
                               BAR(PB_TEMPTY));
     } else {
@@ -1105,10 +1114,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   // VASR_GEMM=tc1 selects the single-CTA kernel
   static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return !(e && strcmp(e, "tc1") == 0); }();
   const bool pair = use_pair && num_sms >= 2;
-  // 192-column tiles (PairCfg<192>) where 128-column ones would end in a 64-column tile: N = 192, 576, ...;
-  // plain projections (optional residual) only.  VASR_TC_T192=0 turns it off.
+  // 192-column tiles (PairCfg<192>).  VASR_TC_T192=0 turns them off.
   static const int t192_env = [] { const char* e = getenv("VASR_TC_T192"); return e ? atoi(e) : 1; }();
-  const bool t192 = pair && t192_env && g.N % 192 == 0 && g.N % TBN != 0 && g.act == ACT_NONE && !g.pe_time && !g.q_scale;
+  // Rule: 192-column tiles whenever N tiles into them without a tile narrower than 128 columns (192, 384, 512 =
+  // 192 + 192 + 128, 576, 768, ...): a 128-column tile is exactly as fast as the control path (768 clocks of MMAs
+  // per k-block against ~770), a 192-column one has 50 % more tensor work per k-block and per A tile loaded and
+  // converted.  Measured against the 128-column tiling (W resident where it applied): in_proj -9 %, x / dt -6 %,
+  // out_proj / ffn2 -18 %, fusion -17 %.  Instantiated for the plain (+ residual), softplus and GELU epilogues.
+  // VASR_TC_T192=2 restricts it to the N that would otherwise end in a 64-column tile.
+  const bool inst192 = !g.pe_time && !g.q_scale && (g.act == ACT_NONE || ((g.act == ACT_SOFTPLUS || g.act == ACT_GELU) && !g.resid));
+  const int64_t r192 = g.N % 192;
+  bool t192 = pair && t192_env && inst192 && (r192 == 0 || r192 >= TBN);
+  if (t192_env == 2 && g.N % TBN == 0) t192 = false;
   const int tn = t192 ? 192 : TBN;
   CUtensorMap tmA, tmWh, tmWl;
   {
@@ -1176,7 +1193,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   };
   if (t192) {
     a.rotate_n = 0;
-    if (rs) go192(gemm_tc2_kernel<ACT_NONE, false, true, false, false, 192>);
+    if (g.act == ACT_SOFTPLUS) go192(gemm_tc2_kernel<ACT_SOFTPLUS, false, false, false, false, 192>);
+    else if (g.act == ACT_GELU) go192(gemm_tc2_kernel<ACT_GELU, false, false, false, false, 192>);
+    else if (rs) go192(gemm_tc2_kernel<ACT_NONE, false, true, false, false, 192>);
     else go192(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 192>);
     if (err != cudaSuccess) return err;
     if (launches) ++*launches;
