@@ -17,9 +17,21 @@ data path.  A "step" is one pass of the whole path over the rank's batch.
            e2e.single_call is one blocking VELOCITYASR.transcribe(host tensor) per step.
   roofline = the selective-scan kernel (the kernel BASELINE.json's metric names): algorithmic
            bytes per launch (4*(4*Di + 2*N) = 6,656 B per token-layer with
-           the silu(z) gate fused) / average launch duration from CUDA events on the launch stream.
+           the silu(z) gate fused) / average launch duration from CUDA events on the launch stream;
+           frac = against the measured HBM copy peak, fp32_issue_frac = against the kernel's real bound
+           (1,152 packed fp32 warp-instructions x 2 clocks per token-layer over 148 x 4 sub-partitions
+           at the SM clock sampled during the run); traffic = DRAM bytes of one launch from the tracked
+           ncu capture profiles/scan_ncu.json (tools/measure_pass.sh regenerates it).
   cpu_baseline = the reference's own PyTorch CPU path (baseline/_ref, kind "reference"; falls
-           back to the numpy oracle port) on a bounded sample, rank 0 at N = 1 only.
+           back to the numpy oracle port) on a bounded sample, rank 0 at N = 1 only; .config1 =
+           BASELINE config 1 (1 x 10 s) in both scan modes.
+  parity  = outside the timed region: the token ids the GPU path produced for the first utterances of
+           input set 0 against the ones the cpu_baseline leg decodes for the same utterances.
+  config.default_scan_mode_ms_per_step = the same step with scan_mode="parallel" (the reference's
+           default semantics, configs/model.yaml:64); the headline uses "sequential" (true recurrence,
+           the reference's fastest CPU mode; its parallel mode cannot run 64 utterances on this host).
+  --global-batch G : strong scaling (BASELINE configs[2]): G utterances split over the ranks.
+  --quantized      : BASELINE configs[4] semantics (quantize.py FakeQuantize model), same timing.
 """
 import argparse
 import json
@@ -150,7 +162,7 @@ def load_reference_impl():
     return "port", None
 
 
-def cpu_path_rtfx(n_utt, seconds, repeats, scan_mode):
+def cpu_path_rtfx(n_utt, seconds, repeats, scan_mode, keep_tokens=False, batch_of=0):
     """Reference CPU path (compute_mel_spectrogram -> model -> ctc_greedy_decode, eval, no_grad,
     all host threads) on n_utt utterances; falls back to the numpy oracle port."""
     import numpy as np
@@ -158,7 +170,8 @@ def cpu_path_rtfx(n_utt, seconds, repeats, scan_mode):
     kind, ref = load_reference_impl()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    audio = synth_audio(n_utt, SR * seconds, 1234)
+    # the first n_utt utterances of the batch the GPU arm times as input set 0 (same generator stream)
+    audio = synth_audio(max(n_utt, batch_of), SR * seconds, 1234)[:n_utt].contiguous()
     best = None
     if ref is not None:
         torch.manual_seed(0)
@@ -177,16 +190,19 @@ def cpu_path_rtfx(n_utt, seconds, repeats, scan_mode):
 
         def run():
             return O.transcribe(a, sd, dict(scan_mode=scan_mode), dtype=np.float32)
-    run()                                   # warm-up (lazy init, thread pools)
+    tokens = run()                          # warm-up (lazy init, thread pools)
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
         run()
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return {"value": n_utt * seconds / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
-            "sample": f"{n_utt} x {seconds} s utterances, scan_mode={scan_mode}, best of {repeats} after 1 warm-up, "
-                      f"{best:.2f} s per pass", "seconds_per_pass": best, "times": times}
+    out = {"value": n_utt * seconds / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+           "sample": f"{n_utt} x {seconds} s utterances, scan_mode={scan_mode}, best of {repeats} after 1 warm-up, "
+                     f"{best:.2f} s per pass", "seconds_per_pass": best, "times": times}
+    if keep_tokens:
+        out["_tokens"] = [list(map(int, t)) for t in tokens]
+    return out
 
 
 def run_reference_arm(args):
@@ -194,8 +210,6 @@ def run_reference_arm(args):
     if rank != 0:
         return
     n_utt = args.ref_utts
-    t_all = []
-    res = None
     kind, ref = load_reference_impl()
     import torch
     cores = os.cpu_count() or 1
@@ -226,12 +240,14 @@ def run_reference_arm(args):
     total = time.perf_counter() - t0
     value = args.steps * n_utt * UTT_SECONDS / total
     sample = (f"each step = {n_utt} of the workload's {BATCH_PER_GPU} utterances (x {UTT_SECONDS} s), "
-              f"scan_mode={SCAN_MODE}, torch CPU, {torch.get_num_threads()} threads")
+              f"scan_mode={SCAN_MODE}, {'torch CPU (unmodified reference)' if ref is not None else 'numpy oracle port'}, "
+              f"{torch.get_num_threads()} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": n_utt, "seconds_per_utterance": UTT_SECONDS,
+        "config": {"workload": WORKLOAD, "batch_per_gpu": n_utt, "global_batch": n_utt,
+                   "seconds_per_utterance": UTT_SECONDS, "tokens_per_utterance": (1 + SR * UTT_SECONDS // 160 + 1) // 2,
                    "scan_mode": SCAN_MODE, "device": "cpu"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
@@ -251,38 +267,97 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+SCAN_NCU = os.path.join(ROOT, "profiles", "scan_ncu.json")
+
+
+def scan_traffic(shape, default_shape):
+    """DRAM bytes (read + write) of ONE launch of the local-layer scan kernel, from the tracked ncu --set full
+    capture profiles/scan_ncu.json (written by tools/ncu_scan_json.py in tools/measure_pass.sh).  The capture is
+    for the default workload; it must exist and match that shape, otherwise the bench stops rather than print a
+    stale number.  Another --batch has no capture: traffic is null."""
+    with open(SCAN_NCU) as fh:
+        cap = json.load(fh)
+    if list(cap["shape"]) != list(default_shape):
+        raise SystemExit(f"bench.py: {SCAN_NCU} was captured for shape {cap['shape']}, the workload is {default_shape}: "
+                         "re-run tools/measure_pass.sh")
+    if list(shape) != list(default_shape):
+        return None, cap
+    return int(cap["dram_bytes_read"]) + int(cap["dram_bytes_write"]), cap
+
+
+def bind_rank_to_cores(local_rank, local_world):
+    """N ranks on one host: give each rank its own slice of the cores the GPU is attached to, so that the copy
+    threads and the list building of 8 ranks do not migrate over (and queue on) the same cores."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+    except Exception:
+        cores = sorted(os.sched_getaffinity(0))
+    cores = [c for c in cores if c in os.sched_getaffinity(0)] or sorted(os.sched_getaffinity(0))
+    per = max(1, len(cores) // max(1, local_world))
+    mine = cores[(local_rank * per) % len(cores):][:per] or cores
+    try:
+        os.sched_setaffinity(0, mine)
+    except Exception:
+        return None
+    return mine
+
+
 def run_own_arm(args):
     import ctypes
     import torch
     import torch.distributed as dist
     import velocity_asr as va
     from velocity_asr import _native
+    from velocity_asr.sharding import gather_transcripts, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    cores = bind_rank_to_cores(local_rank, local_world) if world > 1 else None
+    if world > 1:
+        torch.set_num_threads(max(1, min(4, len(cores) if cores else 4)))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # the one exchange of the design: host-side transcript gather
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    B, S = args.batch, SR * UTT_SECONDS
+    strong = args.global_batch > 0
+    if strong:
+        lo, hi = shard_range(args.global_batch, rank, world)
+        B = hi - lo
+        if args.global_batch % world:
+            raise SystemExit("bench.py: --global-batch must be a multiple of the number of ranks")
+    else:
+        B = args.batch
+    S = SR * UTT_SECONDS
     torch.manual_seed(0)
-    model = va.VELOCITYASR(va.VelocityASRConfig(scan_mode=SCAN_MODE)).to(dev).eval()
-    eng = model._engine(dev)
-    lib = eng.lib
+    model = va.VELOCITYASR(va.VelocityASRConfig(scan_mode=SCAN_MODE))
+    if args.quantized:
+        model = va.prepare_model_for_qat(model)
+    model = model.to(dev).eval()
     # four distinct input sets (4 x 61 MB > the 126 MB L2) rotated across steps; each step also
     # streams > 1 GB of activations, so nothing survives in L2 from one step to the next.
     n_sets = 4
     host = [synth_audio(B, S, 1234 + rank * 16 + i).pin_memory() for i in range(n_sets)]
     devb = [h.to(dev) for h in host]
+    if args.quantized:          # SURVEY 5.8 recipe: calibrate the activation quantisers on one batch of the workload
+        va.calibrate_model(model, [va.compute_mel_spectrogram(devb[0][:8])], device=str(dev))
+    eng = model._engine(dev)
+    lib = eng.lib
     T = 1 + S // 160
     L = (T + 1) // 2
     tokens = torch.empty(B, L, dtype=torch.int32, device=dev)
@@ -290,9 +365,17 @@ def run_own_arm(args):
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
 
-    def step_dev(i):
-        _native.check(lib.vasr_transcribe(eng.handle, _native.ptr(devb[i % n_sets]), B, S, _native.ptr(tokens),
-                                          _native.ptr(lens), sp))
+    def step_dev(i, handle=None):
+        _native.check(lib.vasr_transcribe(handle or eng.handle, _native.ptr(devb[i % n_sets]), B, S,
+                                          _native.ptr(tokens), _native.ptr(lens), sp))
+
+    def timed_steps(handle=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            step_dev(i, handle)
+        e1.record(stream)
+        return e0, e1
 
     # ---- device-resident throughput
     for i in range(args.warmup):
@@ -302,17 +385,20 @@ def run_own_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.vasr_kernel_launches(eng.handle)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
-    e0.record(stream)
-    for i in range(args.steps):
-        step_dev(i)
-    e1.record(stream)
+    e0, e1 = timed_steps()
     barrier()
     sampler.mark_end()
     dev_ms = e0.elapsed_time(e1)
     launches = lib.vasr_kernel_launches(eng.handle) - launches0
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- parity material: what the timed path produces for the first utterances of input set 0
+    step_dev(0)
+    torch.cuda.synchronize()
+    n_par = min(args.cpu_utts, B)
+    tok_h, len_h = tokens[:n_par].cpu().numpy(), lens[:n_par].cpu().tolist()
+    gpu_tokens = [tok_h[b, :n].tolist() for b, n in enumerate(len_h)]
 
     # ---- scan kernel timing (separate pass so event pairs do not perturb the number above)
     lib.vasr_set_timing(eng.handle, 1)
@@ -329,17 +415,20 @@ def run_own_arm(args):
     # ---- end to end through the public API, host buffers in, token lists out.
     # (a) the streaming call: VELOCITYASR.transcribe_batches(iterable of pinned host batches) copies batch i+1
     #     host->device and batch i-1's token ids device->host while batch i computes; every step's H2D and D2H
-    #     are inside the timed region.  (b) one blocking transcribe(host batch) call per step, for reference.
+    #     are inside the timed region.  With N > 1 every step's transcripts are also gathered on the host across
+    #     the ranks (velocity_asr.sharding.gather_transcripts over a gloo group) inside the timed region: the
+    #     design's only exchange.  (b) one blocking transcribe(host batch) call per step.
     for _ in model.transcribe_batches(host[i % n_sets] for i in range(max(2, args.warmup))):
         pass
     barrier()
     t0 = time.perf_counter()
-    n_out = 0
+    n_out = n_all = 0
     for out in model.transcribe_batches(host[i % n_sets] for i in range(args.steps)):
         n_out += len(out)
+        n_all += len(gather_transcripts(out, group=host_group)) if world > 1 else len(out)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert n_out == args.steps * B
+    assert n_out == args.steps * B and n_all == args.steps * B * world
     barrier()
     for i in range(max(1, args.warmup)):
         model.transcribe(host[i % n_sets])
@@ -351,10 +440,27 @@ def run_own_arm(args):
     e2e1_s = time.perf_counter() - t0
     barrier()
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, e2e1_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- the same step under the reference's DEFAULT scan semantics (scan_mode="parallel")
+    par_ms = float("nan")
+    if not args.no_extras:
+        torch.manual_seed(0)
+        model_p = va.VELOCITYASR(va.VelocityASRConfig(scan_mode="parallel"))
+        if args.quantized:
+            model_p = va.prepare_model_for_qat(model_p)
+            model_p._act_qparams = dict(model._act_qparams)
+        model_p = model_p.to(dev).eval()
+        eng_p = model_p._engine(dev)
+        for i in range(args.warmup):
+            step_dev(i, eng_p.handle)
+        barrier()
+        p0, p1 = timed_steps(eng_p.handle)
+        barrier()
+        par_ms = p0.elapsed_time(p1)
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, e2e1_s * 1e3, par_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e1_ms = float(times[0]), float(times[1]), float(times[2])
+    dev_ms, e2e_ms, e2e1_ms, par_ms = (float(t) for t in times)
 
     if rank == 0:
         audio_s = world * B * UTT_SECONDS * args.steps
@@ -363,7 +469,7 @@ def run_own_arm(args):
         # local scan launches come first in each step; the 2 global launches (93 tokens) are tiny
         local_bytes = B * L * 4 * (4 * di + 2 * cfg.ssm_state_dim)
         K1 = min(max(64, L // 8), L)
-        global_bytes = B * K1 * 4 * (4 * di + 2 * cfg.global_ssm_state_dim)
+        global_bytes = B * K1 * 4 * (4 * 2 * cfg.d_model + 2 * cfg.global_ssm_state_dim)
         scan_total_ms = sum(s for s, _ in scan_ms) / len(scan_ms)
         step_total_ms = sum(t for _, t in scan_ms) / len(scan_ms)
         all_bytes = cfg.ssm_layers * local_bytes + cfg.global_ssm_layers * global_bytes
@@ -371,37 +477,70 @@ def run_own_arm(args):
         local_ms = scan_total_ms * (cfg.ssm_layers * local_bytes / all_bytes) / cfg.ssm_layers
         peak, peak_src = hbm_peak()
         achieved = local_bytes / (local_ms * 1e-3) / 1e9
+        traffic, cap = scan_traffic((B, L, di, cfg.ssm_state_dim), (BATCH_PER_GPU, L, di, cfg.ssm_state_dim))
+        # fp32-issue bound: 3 fp32 operations per (state, step) = Di*N*3/2/32 packed warp-instructions per token-layer,
+        # each holding a sub-partition's FMA pipe for 2 clocks; 148 SMs x 4 sub-partitions at the sampled SM clock
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        packed_instr = di * cfg.ssm_state_dim * 3 // 2 // 32
+        issue_floor_ms = B * L * packed_instr * 2 / (148 * 4 * sm_mhz * 1e6) * 1e3
         line = {
             "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.quantized else WORKLOAD + " [quantize.py FakeQuantize model, "
+                       "BASELINE configs[4] semantics]",
+                       "batch_per_gpu": B, "global_batch": B * world,
                        "seconds_per_utterance": UTT_SECONDS, "tokens_per_utterance": L, "scan_mode": SCAN_MODE,
+                       "default_scan_mode_ms_per_step": None if par_ms != par_ms else par_ms / args.steps,
+                       "default_scan_mode": "parallel (configs/model.yaml:64, ssm.py:216-295): same weights and input, "
+                                            "scan_quirk kernel in the 8 local layers",
                        "parallelism": f"dp{world} (utterance shards, no data-path collective)",
                        "l2": "4 rotating input sets (244 MB) + >1 GB of activations per step: larger than L2"},
             "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * L * 4 + B * 4,
                     "api": "VELOCITYASR.transcribe_batches(pinned host batches) -> List[List[int]] per batch "
-                           "(H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i)",
+                           "(H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i)"
+                           + ("; + sharding.gather_transcripts of every step's lists across ranks (gloo, host)"
+                              if world > 1 else ""),
                     "single_call": {"value": audio_s / (e2e1_ms * 1e-3), "ms_per_step": e2e1_ms / args.steps,
                                     "api": "VELOCITYASR.transcribe(pinned host tensor), one blocking call per step"}},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "scan_seq_kernel<LPR=4, 4 warps, 2 rows/lane, structured A> (8 local SSM layers)",
+            "roofline": {"kernel": cap.get("kernel", "scan_seq_kernel") + " (8 local SSM layers)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_full_summary.md
-                         "traffic": 303103232 if (B, L, di, cfg.ssm_state_dim) == (64, 751, 384, 64) else None,
+                         "fp32_issue_frac": issue_floor_ms / local_ms, "fp32_issue_floor_ms": issue_floor_ms,
+                         "fp32_issue_model": f"{packed_instr} packed fp32 warp-instructions x 2 clocks per token-layer / "
+                                             f"(148 SMs x 4 sub-partitions x {sm_mhz:.0f} MHz)",
+                         "traffic": traffic, "traffic_source": os.path.relpath(SCAN_NCU, ROOT) + ": " + cap.get("source", ""),
                          "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": local_ms,
                          "scan_launches_per_step": n_scan, "scan_ms_per_step": scan_total_ms,
                          "scan_share_of_step": scan_total_ms / step_total_ms,
-                         "note": "fp32-issue bound, not HBM bound (DESIGN.md): 24,576 state updates x 3 fp32 ops "
-                                 "per token-layer"},
+                         "note": "the kernel is fp32-issue / shared-memory-delivery bound, not HBM bound (DESIGN.md): "
+                                 "frac is the honest HBM fraction of algorithmic bytes, fp32_issue_frac the fraction of "
+                                 "its real ceiling"},
             "clocks": clocks,
         }
+        if world > 1 and cores:
+            line["config"]["cores_per_rank"] = len(cores)
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_path_rtfx(args.cpu_utts, UTT_SECONDS, 2, SCAN_MODE)
+                base = cpu_path_rtfx(n_par, UTT_SECONDS, 2, SCAN_MODE, keep_tokens=True, batch_of=B)
+                ref_tokens = base.pop("_tokens")
+                line["cpu_baseline"] = base
+                equal = sum(int(a == b) for a, b in zip(gpu_tokens, ref_tokens))
+                line["parity"] = {"utts": len(ref_tokens), "tokens_equal": equal,
+                                  "what": "greedy-CTC token lists of the first utterances of input set 0: the timed GPU "
+                                          f"path vs the cpu_baseline leg ({base['kind']}), outside the timed region"}
+                if args.quantized:
+                    line["parity"]["note"] = "cpu leg runs the FP32 reference model; the GPU arm is the FakeQuantize model"
+                if not args.no_extras:
+                    c1 = {}
+                    for mode in ("sequential", "parallel"):
+                        r = cpu_path_rtfx(1, 10, 3, mode)
+                        c1[mode] = {"value": r["value"], "seconds_per_pass": r["seconds_per_pass"]}
+                    line["cpu_baseline"]["config1"] = dict(
+                        c1, what="BASELINE configs[0]: 1 x 10 s, mel + forward + greedy on the host cores, best of 3")
             except Exception as exc:  # the baseline must never sink the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc!r}"}
@@ -419,8 +558,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU")
     ap.add_argument("--cpu-utts", type=int, default=16, help="utterances in the cpu_baseline sample")
-    ap.add_argument("--ref-utts", type=int, default=8, help="utterances per step of --impl reference")
+    ap.add_argument("--ref-utts", type=int, default=BATCH_PER_GPU,
+                    help="utterances per step of --impl reference (default: the workload's 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the default-scan-mode timing and the config-1 CPU figures")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: this many utterances in total, split over the ranks (configs[2]: 512)")
+    ap.add_argument("--quantized", action="store_true", help="time the FakeQuantize model (configs[4] semantics)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -122,11 +122,69 @@ def test_log_mel_oracle_15s(va, golden):
     assert (mel.std(1) - 1).abs().max() < 1e-4
 
 
-def test_log_mel_rejects_short_and_cpu(va):
+def test_log_mel_rejects_short_and_stages_host_input(va):
     with pytest.raises(RuntimeError):
         va.compute_mel_spectrogram(torch.zeros(1, 150).cuda())     # reflect pad needs > 200 samples
-    with pytest.raises(RuntimeError):
-        va.compute_mel_spectrogram(torch.zeros(1, 16000))          # no CPU path
+    audio = FU.synth_audio(2, 8000, seed=5)
+    host = va.compute_mel_spectrogram(audio)                        # CPU tensor: staged to the GPU, result back on CPU
+    assert host.device.type == "cpu"
+    assert torch.equal(host, va.compute_mel_spectrogram(audio.cuda()).cpu())   # same kernels, same bits
+
+
+def test_reference_smoke_script_sequence_runs_unchanged(va):
+    """/root/reference/test_vel.py:12-47 verbatim in its calls: model, input and logits never leave the CPU
+    on the caller's side (the kernels still run on the GPU: host tensors are staged)."""
+    from velocity_asr import VELOCITYASR, VelocityASRConfig, ctc_greedy_decode
+    config = VelocityASRConfig()
+    model = VELOCITYASR(config)
+    assert model.count_parameters() > 0
+    batch_size, num_frames, mel_bins = 2, 500, 80
+    torch.manual_seed(3)
+    x = torch.randn(batch_size, num_frames, mel_bins)
+    model.eval()
+    with torch.no_grad():
+        logits = model(x)
+    assert logits.device.type == "cpu" and tuple(logits.shape) == (batch_size, (num_frames + 1) // 2, config.vocab_size)
+    decoded = ctc_greedy_decode(logits)
+    assert len(decoded) == batch_size
+    # the staged call is the CUDA call
+    on_gpu = model.cuda()(x.cuda())
+    assert torch.equal(on_gpu.cpu(), logits)
+    assert ctc_greedy_decode(on_gpu) == decoded
+
+
+def test_reference_transcribe_loop_body_runs_unchanged(va):
+    """The body of transcribe_file (scripts/transcribe.py:69-126) with its own calls and argument devices: mel
+    computed from a CPU waveform, moved to the model's device, greedy decode with and without timestamps, word
+    assembly.  Checked against the fused transcribe() and the oracle's run decoder."""
+    from velocity_asr import (VELOCITYASR, VelocityASRConfig, CTCDecoder, compute_mel_spectrogram,
+                              create_default_vocabulary, ctc_greedy_decode_with_timestamps, words_with_timestamps,
+                              frames_to_seconds)
+    from velocity_asr.audio import SAMPLE_RATE, HOP_LENGTH
+    assert (SAMPLE_RATE, HOP_LENGTH) == (16000, 160)
+    device = "cuda"
+    torch.manual_seed(0)
+    model = VELOCITYASR(VelocityASRConfig(scan_mode="sequential"))
+    model.load_state_dict(FU.amplify_state_dict(model.state_dict()))
+    model = model.to(device).eval()
+    decoder = CTCDecoder(create_default_vocabulary(model.config.vocab_size))
+    audio = FU.synth_audio(1, 3 * 16000, seed=17)[0]                # what load_audio returns: 1-D CPU waveform
+    mel = compute_mel_spectrogram(audio)
+    assert mel.device.type == "cpu" and mel.dim() == 2
+    with torch.no_grad():
+        mel_tensor = mel.unsqueeze(0).to(device)
+        logits = model(mel_tensor)
+        tokens, timestamps = ctc_greedy_decode_with_timestamps(logits)[0]
+        text = decoder.decode_greedy(logits)[0]
+    assert tokens == model.transcribe(audio.to(device))[0]
+    o_tokens, o_times = O.ctc_greedy_decode_with_timestamps(logits.cpu().numpy())[0]
+    assert tokens == o_tokens and timestamps == [tuple(t) for t in o_times]
+    assert text == decoder._tokens_to_text(tokens)
+    words = words_with_timestamps(tokens, timestamps, decoder.vocabulary)
+    assert " ".join(w["word"] for w in words).split() == "".join(
+        decoder.vocabulary[t] for t in tokens).replace("▁", " ").split()
+    for w in words:
+        assert 0.0 <= w["start"] <= w["end"] <= frames_to_seconds(logits.size(1))
 
 
 # ------------------------------------------------------------------ selective scan -------
@@ -265,6 +323,18 @@ def test_mamba_mode_equals_sequential(va, golden):
     assert torch.equal(a, b)
 
 
+def decode_with_reference_on_near_ties(va, logits, ref_argmax, safe):
+    """Greedy tokens of OUR logits through OUR decoder, with the frames the reference itself cannot call
+    (best-minus-second margin <= 1e-3 in the reference's own logits) pinned to the reference's choice.  The
+    result must equal the reference's token list unconditionally: every margin-safe frame is ours."""
+    lg = logits.clone()
+    ref = torch.from_numpy(np.asarray(ref_argmax)).to(lg.device).long()
+    unsafe = torch.from_numpy(~np.asarray(safe)).to(lg.device)
+    pinned = torch.full_like(lg, -1e30).scatter_(-1, ref.unsqueeze(-1), 0.0)
+    lg[unsafe] = pinned[unsafe]
+    return va.ctc_greedy_decode(lg)
+
+
 @pytest.mark.parametrize("mode", ["sequential", "parallel"])
 def test_config1_end_to_end(va, golden, mode):
     """BASELINE config 1: 1 x 10 s, mel + forward + greedy."""
@@ -281,8 +351,65 @@ def test_config1_end_to_end(va, golden, mode):
     assert (am == g[mode + "_argmax"])[safe].all()
     assert (am == g[mode + "_argmax"]).mean() >= 0.99
     assert va.ctc_greedy_decode(logits)[0] == m.transcribe(audio)[0]
+    assert safe.mean() > 0.99
+    assert decode_with_reference_on_near_ties(va, logits, g[mode + "_argmax"], safe)[0] == g[mode + "_tokens"].tolist()
     if (am == g[mode + "_argmax"]).all():
         assert m.transcribe(audio)[0] == g[mode + "_tokens"].tolist()
+
+
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_config2_full_batch(va, golden, mode):
+    """BASELINE configs[1], the benchmarked size: the FULL 64 x 15 s seed-1234 batch bench.py times goes through
+    mel + forward + greedy in one call; utterances 0, 31 and 63 are compared with the reference's own output
+    (tests/golden/make_golden_big.py), in the benchmark's scan mode and in the reference's default one."""
+    g = golden("config2")
+    utts = g["utts"].tolist()
+    audio = FU.synth_audio(64, 240000).cuda()
+    m = make_model(va, mode)
+    mel = va.compute_mel_spectrogram(audio)
+    assert np.abs(mel[utts][:, ::50].cpu().numpy() - g["mel_sub"]).max() < MEL_ATOL
+    logits = m(mel)
+    assert logits.shape == (64, 751, 1000)
+    ours = logits[utts]
+    assert rel(ours[:, ::25], g[mode + "_logits_sub"]) < LOGIT_RTOL
+    am = ours.argmax(-1).cpu().numpy()
+    safe = g[mode + "_margin"] > 1e-3
+    assert safe.mean() > 0.99
+    assert (am == g[mode + "_argmax"])[safe].all()
+    tokens = m.transcribe(audio)                         # the fused call the benchmark times
+    assert tokens == va.ctc_greedy_decode(logits)
+    pinned = decode_with_reference_on_near_ties(va, ours, g[mode + "_argmax"], safe)
+    for row, want in zip(pinned, g[mode + "_tokens"]):
+        assert row == [t for t in want.tolist() if t >= 0]
+    agree = np.mean([tokens[u] == [t for t in want.tolist() if t >= 0] for u, want in zip(utts, g[mode + "_tokens"])])
+    assert agree >= 2 / 3                                # bit-exact unless a near-tie frame flipped
+
+
+def test_config4_long_form(va, golden):
+    """BASELINE configs[3] at reduced batch: one 600 s utterance = 30,001 tokens (1,876 scan chunks of 16 steps,
+    K1 = 3,750 pooled tokens, K2 = 64 attention keys), positional table regenerated to 30,008 rows by the
+    formula of model.py:94-100, against the reference's own sequential-scan output."""
+    g = golden("config4")
+    audio = FU.synth_audio(1, 600 * 16000, seed=int(g["seed"])).cuda()
+    m = make_model(va, "sequential")
+    with pytest.raises(RuntimeError):
+        m.transcribe(audio)                              # the stock 5,000-row table is too short (model.py:125)
+    m.extend_positional_table(int(g["rows"]))
+    mel = va.compute_mel_spectrogram(audio)
+    logits, feats = m(mel, return_features=True)
+    assert logits.shape == (1, 30001, 1000)
+    idx = torch.from_numpy(g["token_idx"]).cuda()
+    scale = np.abs(g["local_at"]).max()
+    assert np.abs(feats["local_features"][0, idx].cpu().numpy() - g["local_at"]).max() / scale < LOGIT_RTOL
+    assert np.abs(feats["local_features"][0, -1].cpu().numpy() - g["local_last"]).max() / scale < LOGIT_RTOL
+    assert rel(feats["fused_features"][0, idx], g["fused_at"]) < LOGIT_RTOL
+    assert rel(logits[0, idx], g["logits_at"]) < LOGIT_RTOL
+    am = logits.argmax(-1).cpu().numpy()
+    safe = g["margin"] > 1e-3
+    assert safe.mean() > 0.99
+    assert (am == g["argmax"])[safe].all()
+    assert decode_with_reference_on_near_ties(va, logits, g["argmax"], safe)[0] == g["tokens"].tolist()
+    assert m.transcribe(audio) == va.ctc_greedy_decode(logits)
 
 
 def test_transcribe_paths_agree_and_shard(va):

@@ -69,7 +69,7 @@ def test_vocabulary_and_text(va):
 
 
 def test_frontend_tables_match_reference_fixture(va, golden):
-    from velocity_asr.frontend import frontend_tables
+    from velocity_asr.audio import frontend_tables
     g = golden("frontend")
     fb, win = frontend_tables(80)
     assert (fb.numpy() == g["filterbank"]).all()       # same torch float32 ops -> same bits
@@ -98,9 +98,25 @@ def test_fails_loudly_without_cuda(va):
     h = ctypes.c_void_p()
     rc = _native.lib().vasr_create(ctypes.byref(cfg), 0, ctypes.byref(h))
     assert rc == _native.ERR_CUDA and b"no CPU path" in _native.lib().vasr_last_error()
-    with pytest.raises(RuntimeError):
+    # host tensors are staged to a CUDA device, never computed on the CPU: without a device every call raises
+    with pytest.raises(RuntimeError, match="no CPU path"):
         va.VELOCITYASR()(torch.zeros(1, 10, 80))
     with pytest.raises(RuntimeError):
         va.compute_mel_spectrogram(torch.zeros(16000))
     with pytest.raises(RuntimeError):
         va.ctc_greedy_decode(torch.zeros(1, 5, 10))
+
+
+def test_word_assembly_follows_the_reference_script(va):
+    """scripts/transcribe.py:80-126 on a hand-made token stream: a word ends at the END frame of the separator
+    that closes it, the last word at the end of the last token; leading / repeated separators add nothing."""
+    vocab = va.create_default_vocabulary(100)
+    t = {ch: vocab.index(ch) for ch in "hi yo"}
+    tokens = [t[" "], t["h"], t["i"], t[" "], t[" "], t["y"], t["o"]]
+    stamps = [(0, 1), (2, 3), (3, 5), (6, 8), (9, 10), (11, 12), (14, 17)]
+    words = va.words_with_timestamps(tokens, stamps, vocab)
+    sec = va.frames_to_seconds
+    assert words == [{"word": "hi", "start": sec(2), "end": sec(8)}, {"word": "yo", "start": sec(11), "end": sec(17)}]
+    assert sec(50) == 1.0                                  # 50 tokens = 100 mel frames = 1 s
+    assert va.words_with_timestamps([], [], vocab) == []
+    assert va.words_with_timestamps([1000], [(0, 1)], vocab)[0]["word"] == "<unk>"

@@ -198,3 +198,23 @@ def test_quantized_forward_matches_reference(golden):
     assert np.abs(g["logits_q"] - g["logits_fp32"]).max() > 5 * step       # quantisation is visible
     wq = O.quantized_weight(sd["ctc_head.proj.2.weight"].astype(np.float64))[:8]
     assert np.abs(wq - g["wq_ctc_rows"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("mode", ["sequential", "parallel"])
+def test_config2_utterance_at_benchmark_size(golden, mode):
+    """BASELINE configs[1] size: utterance 31 of the seed-1234 64 x 15 s batch (751 tokens) through the oracle,
+    against the reference's own output at that size (tests/golden/make_golden_big.py), both scan semantics."""
+    g = golden("config2")
+    row = g["utts"].tolist().index(31)
+    audio = FU.synth_audio(64, 240000)[31:32].numpy()
+    mel = O.log_mel(audio)
+    assert np.abs(mel[:, ::50] - g["mel_sub"][row:row + 1]).max() < 1e-4
+    sd = {k: v.numpy() for k, v in seeded_state_dict().items()}
+    logits = O.forward(mel, sd, dict(scan_mode=mode))
+    assert logits.shape == (1, 751, 1000)
+    assert rel(logits[:, ::25], g[mode + "_logits_sub"][row:row + 1]) < 1e-3
+    safe = g[mode + "_margin"][row] > 1e-3
+    assert (logits.argmax(-1)[0] == g[mode + "_argmax"][row])[safe].all()
+    if safe.all():
+        want = [t for t in g[mode + "_tokens"][row].tolist() if t >= 0]
+        assert O.ctc_greedy_decode(logits)[0] == want

@@ -135,6 +135,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// Tuning / debugging switches read from the environment exist only in a -DVASR_DEBUG build; the shipped library
+// has ONE code path per operation (the defaults below are compiled in).  VASR_PDL (pure scheduling change, kept
+// with a bit-identity test) and VASR_LIB (which build the Python binding loads) are the only run-time switches.
+#ifdef VASR_DEBUG
+inline int debug_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+inline int debug_env_int(const char*, int dflt) { return dflt; }
+#endif
+
 // host: launch with the programmatic-serialisation attribute (VASR_PDL=0 turns it off)
 inline bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("VASR_PDL"); return !(e && e[0] == '0'); }();

@@ -40,12 +40,12 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int N_FFT = 400, HOP = 160, N_FREQ = 201, PAD = 200;
-constexpr int SPEC_LD = 404;  // 2*201 rounded up to a multiple of 4 (vector stores)
 
 struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *conv_w, *conv_b, *A, *D;
   float *w_in, *w_xdt, *b_xdt, *w_out, *w_f1, *b_f1, *w_f2, *b_f2;
   int N = 0;
+  int di = 0, ks = 0;      // d_inner and depthwise kernel size of THIS stack (GlobalSSM hard-codes 2 / 4: ssm.py:529-538)
   int structured = 0;
 };
 
@@ -108,22 +108,23 @@ struct vasr_handle {
   float *w_q = nullptr, *b_q = nullptr, *w_kv = nullptr, *b_kv = nullptr, *w_o = nullptr, *b_o = nullptr;
   float *w_f3 = nullptr, *b_f3 = nullptr, *w_fo = nullptr, *b_fo = nullptr;
   float *ctc_g = nullptr, *ctc_b = nullptr, *w_ctc = nullptr, *b_ctc = nullptr;
-  float* dft_w = nullptr;    // [hann*cos | hann*sin] table of the dense-DFT route (VASR_MEL=dft)
   float* win = nullptr;      // analysis window (400)
   float* tw400 = nullptr;    // W400^m = (cos, -sin)(2 pi m / 400)
-  int mel_dft = 0;           // VASR_MEL=dft: first-version route (DFT as a strided projection), kept for A/B runs
   int *fb_lo = nullptr, *fb_off = nullptr;
   float* fb_w = nullptr;
 
   int num_sms = 148;
-  int use_tc = 1;          // VASR_GEMM=simt forces the CUDA-core projection kernel
-  int dft_tc = 0;          // VASR_DFT=tc runs the windowed DFT on the tensor-core kernel (fails the 1e-4 mel bar:
-                           // the MMA's fp32 accumulation over 400 terms is not accurate enough for weak bins)
   int64_t tc_launches = 0;
 
   Arena ws;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
+  // Calls on one handle share the workspace and the lazily built weight splits.  Each call leaves an event at
+  // its end on its stream; a call arriving on ANOTHER stream (the *_host entry points use own_stream) waits for
+  // it on the device before touching either, so an asynchronous forward followed by a host transcribe is ordered.
+  cudaEvent_t call_done = nullptr;
+  cudaStream_t call_stream = nullptr;
+  bool call_pending = false;
 
   // VASR_PROF=1: CUDA-event pairs around every projection launch, aggregated by shape (tools/gemm_profile.py)
   int prof = 0;
@@ -140,9 +141,12 @@ struct vasr_handle {
 namespace {
 
 struct Dims {
-  int64_t B, S, T, L, M, K1, K2, Mg, M2, Tp, ldp;
+  int64_t B, S, T, L, M, K1, K2, Mg, M2, Tp;
   int d, di, n_mels, V, att;
 };
+
+// GlobalSSM is built with expand_ratio = 2 and kernel_size = 4 whatever the config says (ssm.py:529-538)
+constexpr int GLOBAL_EXPAND = 2, GLOBAL_KS = 4;
 
 Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
   Dims q{};
@@ -159,9 +163,9 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
   q.Mg = B * q.K1;
   q.M2 = B * q.K2;
   q.Tp = T + 2 + ((T + 2) & 1);                       // even: batch stride is a multiple of the 2-frame row stride
-  q.ldp = ((S + 2 * PAD + HOP - 1) / HOP) * HOP;      // multiple of the hop: same for the STFT frame view
   q.d = h->cfg.d_model;
-  q.di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
+  // widest d_inner of the two stacks: sizes the buffers both share
+  q.di = h->cfg.d_model * (h->cfg.ssm_expand_ratio > GLOBAL_EXPAND ? h->cfg.ssm_expand_ratio : GLOBAL_EXPAND);
   q.n_mels = h->cfg.mel_bins;
   q.V = h->cfg.vocab_size;
   q.att = h->cfg.attention_dim;
@@ -169,7 +173,7 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
 }
 
 struct Work {
-  float *xp, *spec, *raw, *mean, *rstd, *melpad;
+  float *raw, *mean, *rstd, *melpad;
   double* part;
   float* qscratch;      // probe output of a quantised projection during calibration (M x max N)
   float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
@@ -190,10 +194,6 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   const int nmax = h->cfg.ssm_state_dim > h->cfg.global_ssm_state_dim ? h->cfg.ssm_state_dim
                                                                       : h->cfg.global_ssm_state_dim;
   if (need_mel) {
-    if (h->mel_dft) {
-      t.xp = a.take<float>(q.B * q.ldp);
-      t.spec = a.take<float>(q.B * q.T * SPEC_LD);
-    }
     t.part = a.take<double>(q.B * mel_fft_blocks(q.T) * q.n_mels * 2);
     t.raw = a.take<float>(q.B * q.T * q.n_mels);
     t.mean = a.take<float>(q.B * q.n_mels);
@@ -316,9 +316,11 @@ int up_w(vasr_handle* h, const std::string& k, int64_t numel, int64_t rows, floa
   return upload(h, w.data(), w.size(), dst);
 }
 
-int pack_block(vasr_handle* h, const std::string& p, int N, BlockW* w) {
-  const int d = h->cfg.d_model, di = d * h->cfg.ssm_expand_ratio, ks = h->cfg.ssm_kernel_size;
+int pack_block(vasr_handle* h, const std::string& p, int N, int expand, int ks, BlockW* w) {
+  const int d = h->cfg.d_model, di = d * expand;
   w->N = N;
+  w->di = di;
+  w->ks = ks;
   RET(up(h, p + "norm1.weight", d, &w->ln1_g));
   RET(up(h, p + "norm1.bias", d, &w->ln1_b));
   RET(up(h, p + "norm2.weight", d, &w->ln2_g));
@@ -407,15 +409,6 @@ int pack_frontend_impl(vasr_handle* h) {
   } else {
     default_filterbank(n_mels, fb);
   }
-  // DFT table rows: k in [0,201): win[n] cos(2 pi k n / 400); 201 + k: win[n] sin(...)
-  std::vector<float> tab((size_t)SPEC_LD * N_FFT, 0.f);   // 402 rows + 2 zero rows (N % 4 == 0 for the tensor-core path)
-  for (int k = 0; k < N_FREQ; ++k)
-    for (int n = 0; n < N_FFT; ++n) {
-      const double ang = 2.0 * M_PI * (double)((k * n) % N_FFT) / (double)N_FFT;
-      tab[(size_t)k * N_FFT + n] = (float)((double)win[n] * cos(ang));
-      tab[(size_t)(N_FREQ + k) * N_FFT + n] = (float)((double)win[n] * sin(ang));
-    }
-  RET(upload(h, tab.data(), tab.size(), &h->dft_w));
   RET(upload(h, win.data(), win.size(), &h->win));
   std::vector<float> tw((size_t)2 * N_FFT);
   for (int m = 0; m < N_FFT; ++m) {
@@ -518,18 +511,19 @@ int gemm(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
   return r;
 }
 
+// Every projection of the model runs on the tcgen05 kernel; a view it cannot take (alignment, tensor-map limits)
+// is an error, never a silent change of kernel.
 int gemm_impl(vasr_handle* h, GemmArgs& g, cudaStream_t s) {
-  if (h->use_tc && (!g.blocked_sum || h->dft_tc)) {
-    RET(split_of(h, g.W, g.N * g.K, s, &g.W_split));
-    cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
-    if (e == cudaSuccess) {
-      ++h->tc_launches;
-      return VASR_OK;
-    }
-    if (e != cudaErrorNotSupported) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
+  RET(split_of(h, g.W, g.N * g.K, s, &g.W_split));
+  const cudaError_t e = launch_gemm_tc(g, h->num_sms, s, &h->launches);
+  if (e == cudaErrorNotSupported) {
     (void)cudaGetLastError();
+    return fail(VASR_ERR_UNSUPPORTED, "projection " + std::to_string(g.M) + " x " + std::to_string(g.K) + " -> " +
+                                          std::to_string(g.N) + ": view not supported by the tensor-core kernel "
+                                          "(16-byte alignment of rows, K % 4, N % 4)");
   }
-  KL(launch_gemm(g, s, &h->launches));
+  if (e != cudaSuccess) return fail(VASR_ERR_CUDA, std::string("launch_gemm_tc: ") + cudaGetErrorString(e));
+  ++h->tc_launches;
   return VASR_OK;
 }
 
@@ -555,7 +549,7 @@ int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const fl
 
 
 int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t L, int quirk, cudaStream_t s) {
-  const int di = h->cfg.d_model * h->cfg.ssm_expand_ratio;
+  const int di = w.di;
   const int64_t ld = 2 * w.N + di;
   ScanArgs a;
   a.x = k.xz; a.ldx = 2 * di;
@@ -581,10 +575,9 @@ int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t 
 // SSMBlock._forward_impl (ssm.py:404-427): x (M, d) in k.xa -> result in k.xa; xb/u/xz/... scratch
 int run_block(vasr_handle* h, const BlockW& w, const Work& k, float* x, float* x1, int64_t B, int64_t L, int quirk,
               cudaStream_t s) {
-  const int d = h->cfg.d_model, di = d * h->cfg.ssm_expand_ratio;
+  const int d = h->cfg.d_model, di = w.di;
   const int64_t M = B * L;
-  KL(launch_ln_dwconv(x, k.u, w.ln1_g, w.ln1_b, w.conv_w, w.conv_b, B, L, d, h->cfg.ssm_kernel_size, s,
-                      &h->launches));
+  KL(launch_ln_dwconv(x, k.u, w.ln1_g, w.ln1_b, w.conv_w, w.conv_b, B, L, d, w.ks, s, &h->launches));
   RET(linear(h, k.u, d, w.w_in, nullptr, k.xz, 2 * di, M, d, 2 * di, ACT_NONE, 0, nullptr, 0, s));
   RET(linear(h, k.xz, 2 * di, w.w_xdt, w.b_xdt, k.bcdt, 2 * w.N + di, M, di, 2 * w.N + di, ACT_SOFTPLUS, 2 * w.N,
              nullptr, 0, s));
@@ -660,24 +653,9 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
 
 // PCM (device) -> k.raw (+ mean/rstd when normalize)
 int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int normalize, cudaStream_t s) {
-  if (!h->mel_dft) {
-    KL(launch_mel_fft(pcm, k.raw, normalize ? k.part : nullptr, q.B, q.S, q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w,
-                      h->win, h->tw400, s, &h->launches, k.rag));
-    if (normalize)
-      KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
-    return VASR_OK;
-  }
-  if (k.rag) return fail(VASR_ERR_UNSUPPORTED, "ragged batches need the FFT mel path (unset VASR_MEL=dft)");
-  KL(launch_reflect_pad(pcm, k.xp, q.B, q.S, PAD, q.ldp, s, &h->launches));
-  GemmArgs g;
-  g.A = k.xp; g.lda = HOP; g.rows_per_batch = q.T; g.batch_stride = q.ldp;
-  g.W = h->dft_w; g.C = k.spec; g.ldc = SPEC_LD;
-  g.M = q.B * q.T; g.N = SPEC_LD; g.K = N_FFT;
-  g.blocked_sum = 1;
-  RET(gemm(h, g, s));
-  KL(launch_mel_log(k.spec, SPEC_LD, k.raw, q.B * q.T, N_FREQ, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, s,
-                    &h->launches));
-  if (normalize) KL(launch_mel_stats(k.raw, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches));
+  KL(launch_mel_fft(pcm, k.raw, normalize ? k.part : nullptr, q.B, q.S, q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w,
+                    h->win, h->tw400, s, &h->launches, k.rag));
+  if (normalize) KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
   return VASR_OK;
 }
 
@@ -687,10 +665,37 @@ int check_ready(const vasr_handle* h) {
   return VASR_OK;
 }
 
-int bind_device(const vasr_handle* h) {
-  CK(cudaSetDevice(h->device));
-  return VASR_OK;
-}
+// Binds the handle's device for the duration of one entry point and puts the caller's device back afterwards
+// (a model on cuda:1 must not move a single-process multi-GPU program's current device).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess || prev == dev) prev = -1;
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Orders one workspace-using call after the previous one on the same handle (see vasr_handle::call_done).
+struct CallOrder {
+  vasr_handle* h;
+  cudaStream_t s;
+  CallOrder(vasr_handle* h_, cudaStream_t s_) : h(h_), s(s_) {
+    if (h->call_pending && h->call_stream != s) cudaStreamWaitEvent(s, h->call_done, 0);
+  }
+  ~CallOrder() {
+    if (cudaEventRecord(h->call_done, s) == cudaSuccess) {
+      h->call_stream = s;
+      h->call_pending = true;
+    }
+  }
+  CallOrder(const CallOrder&) = delete;
+  CallOrder& operator=(const CallOrder&) = delete;
+};
 
 void timing_begin(vasr_handle* h, cudaStream_t s) {
   h->ev_used = 0;
@@ -776,11 +781,13 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   if (!n_ok(c.ssm_state_dim) || !n_ok(c.global_ssm_state_dim))
     return fail(VASR_ERR_UNSUPPORTED, "ssm state_dim must be 16, 32 or 64");
   const int di = c.d_model * c.ssm_expand_ratio;
-  if (c.ssm_expand_ratio < 1 || (di % 64) != 0) return fail(VASR_ERR_UNSUPPORTED, "d_model*expand_ratio must be a multiple of 64");
+  if (c.ssm_expand_ratio < 1 || (di % 64) != 0 || (c.d_model * GLOBAL_EXPAND) % 64 != 0)
+    return fail(VASR_ERR_UNSUPPORTED, "d_model*expand_ratio (and 2*d_model for the global stack) must be multiples of 64");
   if (c.ssm_kernel_size < 1 || c.ssm_kernel_size > 8) return fail(VASR_ERR_UNSUPPORTED, "ssm_kernel_size must be in [1, 8]");
   if (c.attention_heads < 1 || c.attention_dim % c.attention_heads != 0 || c.attention_dim / c.attention_heads > 16 ||
-      c.attention_dim % 16 != 0 || c.attention_heads * 64 > 1024)
-    return fail(VASR_ERR_UNSUPPORTED, "attention_dim must be a multiple of 16 with head_dim <= 16");
+      c.attention_dim % 16 != 0 || c.attention_heads > 4)
+    return fail(VASR_ERR_UNSUPPORTED, "attention_dim must be a multiple of 16 with head_dim <= 16 and at most 4 heads "
+                                      "(the attention kernel runs 64 threads per head in a 256-thread CTA)");
   if (c.vocab_size < 1 || c.ssm_layers < 0 || c.global_ssm_layers < 0) return fail(VASR_ERR_INVALID, "bad sizes");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
@@ -789,16 +796,14 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(VASR_ERR_CUDA, std::string("libvasr is built for sm_100a only; device is ") + prop.name);
-  CK(cudaSetDevice(device));
+  DeviceGuard dev_guard(device);
   vasr_handle* h = new vasr_handle();
   h->cfg = c;
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  if (const char* ev = getenv("VASR_GEMM")) h->use_tc = strcmp(ev, "simt") != 0;
-  if (const char* ev = getenv("VASR_DFT")) h->dft_tc = strcmp(ev, "tc") == 0;
-  if (const char* ev = getenv("VASR_MEL")) h->mel_dft = strcmp(ev, "dft") == 0;
-  if (const char* ev = getenv("VASR_PROF")) h->prof = atoi(ev);
+  h->prof = debug_env_int("VASR_PROF", 0);
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->call_done, cudaEventDisableTiming));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   CK(cudaEventCreate(&h->ev_t0));
@@ -810,7 +815,7 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
 
 void vasr_destroy(vasr_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard dev_guard(h->device);
   cudaDeviceSynchronize();
   free_weights(h);
   for (void* p : h->frontend_allocs) cudaFree(p);
@@ -820,6 +825,7 @@ void vasr_destroy(vasr_handle* h) {
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->call_done) cudaEventDestroy(h->call_done);
   for (int i = 0; i < vasr_handle::RAG_RING; ++i) {
     if (h->rag_pin[i]) cudaFreeHost(h->rag_pin[i]);
     if (h->rag_ev[i]) cudaEventDestroy(h->rag_ev[i]);
@@ -836,7 +842,7 @@ int vasr_set_weight(vasr_handle* h, const char* name, const float* host, int64_t
   if (!ok) return fail(VASR_ERR_INVALID, "unknown weight name: " + k);
   h->staged[k].assign(host, host + numel);
   if (k.rfind("frontend.", 0) == 0) {  // front-end tables take effect at once, model weights at commit
-    RET(bind_device(h));
+    DeviceGuard dev_guard(h->device);
     return pack_frontend(h);
   }
   h->committed = false;
@@ -845,11 +851,11 @@ int vasr_set_weight(vasr_handle* h, const char* name, const float* host, int64_t
 
 int vasr_commit_weights(vasr_handle* h) {
   if (!h) return fail(VASR_ERR_INVALID, "null handle");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   CK(cudaDeviceSynchronize());
   free_weights(h);
   const vasr_config& c = h->cfg;
-  const int d = c.d_model, di = d * c.ssm_expand_ratio, nm = c.mel_bins, att = c.attention_dim;
+  const int d = c.d_model, nm = c.mel_bins, att = c.attention_dim;
   // temporal binding: conv.weight (d, mel, 3) -> (d, 3*mel) with k index = tap*mel + channel
   std::vector<float> cwv;
   RET(get_w(h, "temporal_binding.conv.weight", (int64_t)d * nm * 3, d, &cwv));
@@ -870,13 +876,15 @@ int vasr_commit_weights(vasr_handle* h) {
   RET(up(h, "temporal_binding.norm.bias", d, &h->tb_bt));
   h->local.resize(c.ssm_layers);
   for (int i = 0; i < c.ssm_layers; ++i)
-    RET(pack_block(h, "local_ssm.layers." + std::to_string(i) + ".", c.ssm_state_dim, &h->local[i]));
+    RET(pack_block(h, "local_ssm.layers." + std::to_string(i) + ".", c.ssm_state_dim, c.ssm_expand_ratio,
+                   c.ssm_kernel_size, &h->local[i]));
   RET(up(h, "local_ssm.norm.weight", d, &h->loc_g));
   RET(up(h, "local_ssm.norm.bias", d, &h->loc_b));
   const std::string gc = "global_context.";
   h->global.resize(c.global_ssm_layers);
   for (int i = 0; i < c.global_ssm_layers; ++i)
-    RET(pack_block(h, gc + "global_ssm.layers." + std::to_string(i) + ".", c.global_ssm_state_dim, &h->global[i]));
+    RET(pack_block(h, gc + "global_ssm.layers." + std::to_string(i) + ".", c.global_ssm_state_dim, GLOBAL_EXPAND,
+                   GLOBAL_KS, &h->global[i]));
   RET(up(h, gc + "global_ssm.norm.weight", d, &h->glo_g));
   RET(up(h, gc + "global_ssm.norm.bias", d, &h->glo_b));
   RET(up_w(h, gc + "pool1.pool_proj.weight", (int64_t)d * d, d, &h->p1_w));
@@ -942,8 +950,9 @@ int vasr_log_mel(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int
   if (!h) return fail(VASR_ERR_INVALID, "null handle");
   if (B < 0 || !pcm_dev || !mel_dev) return fail(VASR_ERR_INVALID, "null argument");
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, S, vasr_num_frames(S));
   Work k;
   RET(ensure_workspace(h, q, true, false, &k));
@@ -957,8 +966,9 @@ int vasr_forward(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, flo
                  float* feat_local_dev, float* feat_fused_dev, void* stream) {
   RET(check_ready(h));
   if (B < 0 || T < 1 || !mel_dev || !logits_dev) return fail(VASR_ERR_INVALID, "null argument");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, 0, T);
   Work k;
   RET(ensure_workspace(h, q, false, false, &k));
@@ -976,8 +986,9 @@ int vasr_ssm_block(vasr_handle* h, int stack, int layer, int scan_mode, const fl
   const std::vector<BlockW>& blocks = stack == 0 ? h->local : h->global;
   if (layer < 0 || layer >= (int)blocks.size()) return fail(VASR_ERR_INVALID, "layer out of range");
   if (scan_mode > 2) return fail(VASR_ERR_INVALID, "Unknown scan_mode");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   Dims q = make_dims(h, B, 0, 2 * L - 1);
   Work k;
   RET(ensure_workspace(h, q, false, false, &k));
@@ -990,8 +1001,9 @@ int vasr_ssm_block(vasr_handle* h, int stack, int layer, int scan_mode, const fl
 
 int vasr_global_context(vasr_handle* h, const float* local_dev, int64_t B, int64_t L, float* out_dev, void* stream) {
   RET(check_ready(h));
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   Dims q = make_dims(h, B, 0, 2 * L - 1);
   Work k;
   RET(ensure_workspace(h, q, false, false, &k));
@@ -1004,8 +1016,9 @@ int vasr_global_context(vasr_handle* h, const float* local_dev, int64_t B, int64
 
 int vasr_ctc_head(vasr_handle* h, const float* x_dev, int64_t B, int64_t L, float* logits_dev, void* stream) {
   RET(check_ready(h));
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   Dims q = make_dims(h, B, 0, 2 * L - 1);
   Work k;
   RET(ensure_workspace(h, q, false, false, &k));
@@ -1134,6 +1147,7 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
                            int32_t* tokens_dev, int32_t* lens_dev, int32_t* tokens_host, int32_t* lens_host,
                            cudaStream_t s, const int32_t* sample_lens = nullptr) {
   const bool host = pcm_host != nullptr;
+  CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, S, vasr_num_frames(S));
   Work k;
   RET(ensure_workspace(h, q, true, true, &k, host));
@@ -1164,7 +1178,7 @@ int vasr_transcribe(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, 
   RET(check_ready(h));
   if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev) return fail(VASR_ERR_INVALID, "null argument");
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   return transcribe_impl(h, pcm_dev, nullptr, B, S, tokens_dev, lens_dev, nullptr, nullptr,
                          static_cast<cudaStream_t>(stream));
 }
@@ -1174,7 +1188,7 @@ int vasr_transcribe_host(vasr_handle* h, const float* pcm_host, int64_t B, int64
   RET(check_ready(h));
   if (B <= 0 || !pcm_host || !tokens_host || !lens_host) return fail(VASR_ERR_INVALID, "null argument");
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   return transcribe_impl(h, nullptr, pcm_host, B, S, nullptr, nullptr, tokens_host, lens_host, h->own_stream);
 }
 
@@ -1184,7 +1198,7 @@ int vasr_transcribe_ragged(vasr_handle* h, const float* pcm_dev, const int32_t* 
   if (B < 0 || !pcm_dev || !tokens_dev || !lens_dev || !sample_lens_host)
     return fail(VASR_ERR_INVALID, "null argument");
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   return transcribe_impl(h, pcm_dev, nullptr, B, S, tokens_dev, lens_dev, nullptr, nullptr,
                          static_cast<cudaStream_t>(stream), sample_lens_host);
 }
@@ -1195,7 +1209,7 @@ int vasr_transcribe_ragged_host(vasr_handle* h, const float* pcm_host, const int
   if (B <= 0 || !pcm_host || !tokens_host || !lens_host || !sample_lens_host)
     return fail(VASR_ERR_INVALID, "null argument");
   if (S <= PAD) return fail(VASR_ERR_SHAPE, "reflect padding needs more than 200 samples (audio.py:100-101)");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   return transcribe_impl(h, nullptr, pcm_host, B, S, nullptr, nullptr, tokens_host, lens_host, h->own_stream,
                          sample_lens_host);
 }
@@ -1204,8 +1218,9 @@ int vasr_forward_ragged(vasr_handle* h, const float* mel_dev, const int32_t* fra
                         float* logits_dev, void* stream) {
   RET(check_ready(h));
   if (B < 0 || T < 1 || !mel_dev || !logits_dev || !frame_lens_host) return fail(VASR_ERR_INVALID, "null argument");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, 0, T);
   Work k;
   RET(ensure_workspace(h, q, false, false, &k));
@@ -1241,8 +1256,9 @@ int vasr_calibrate(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, v
   RET(check_ready(h));
   if (!h->quant_active) return fail(VASR_ERR_STATE, "quantisation is not enabled (vasr_set_quantization + commit)");
   if (B <= 0 || T < 1 || !mel_dev) return fail(VASR_ERR_INVALID, "null argument");
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, 0, T);
   Work k;
   RET(ensure_workspace(h, q, false, true, &k));
@@ -1259,7 +1275,7 @@ int vasr_get_quant_params(vasr_handle* h, const char* module, float* scale, floa
   int j = 0;
   QSite* q = find_module(h, module, &j);
   if (!q) return fail(VASR_ERR_INVALID, std::string("not a quantised module: ") + module);
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(scale, q->qs + q->c0[j], sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(zero_point, q->qz + q->c0[j], sizeof(float), cudaMemcpyDeviceToHost));
@@ -1272,7 +1288,7 @@ int vasr_set_quant_params(vasr_handle* h, const char* module, float scale, float
   int j = 0;
   QSite* q = find_module(h, module, &j);
   if (!q) return fail(VASR_ERR_INVALID, std::string("not a quantised module: ") + module);
-  RET(bind_device(h));
+  DeviceGuard dev_guard(h->device);
   CK(cudaDeviceSynchronize());
   std::vector<float> sv((size_t)q->nc[j], scale), zv((size_t)q->nc[j], zero_point);
   CK(cudaMemcpy(q->qs + q->c0[j], sv.data(), sv.size() * sizeof(float), cudaMemcpyHostToDevice));

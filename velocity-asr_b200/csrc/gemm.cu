@@ -1,8 +1,8 @@
-// gemm.cu — fp32 projection kernel: C = epi(A · Wᵀ), both operands K-contiguous.
+// gemm.cu — fp32 CUDA-core projection kernel: C = epi(A · Wᵀ), both operands K-contiguous.
 //
-// Replaces every F.linear / Conv1d-as-GEMM on the hot path of the reference
-// (ssm.py:105-113,130,394-400; model.py:187-190,223-227; attention.py:76,139-141,162,207-218).
-// CUDA-core path in full fp32 (FFMA2: two fp32 FMAs per issue slot, paired along k so no
+// The operator behind vasr_linear (include/vasr.h): a general F.linear for views the tensor-core kernel
+// (gemm_tc.cu) cannot take.  The model's own launch sequence runs every projection on gemm_tc.cu and never
+// comes here.  Full fp32 (FFMA2: two fp32 FMAs per issue slot, paired along k so no
 // operand duplication is needed); results sit within a few ulp of the reference's SGEMM,
 // which is what keeps argmax token ids stable.  128x64x16 tiles, 256 threads, 8x4 outputs per
 // thread, double-buffered shared memory with register-staged global prefetch.
@@ -18,11 +18,7 @@ constexpr int LDT = BK + 2;  // 18-float rows: 8-byte LDS of 16 rows hit 32 dist
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// BLOCKED: every 16-wide k tile is summed into fresh registers and then added to the running
-// total (two-level summation).  Used for the 400-term DFT rows, where plain running sums lose
-// ~sqrt(K) ulps and the log of a weak mel bin amplifies it past the 1e-4 mel tolerance.
-template <bool BLOCKED>
-__global__ void __launch_bounds__(256, BLOCKED ? 1 : 2) gemm_tn_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(256, 2) gemm_tn_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[2][BM * LDT];
   __shared__ __align__(16) float Bs[2][BN * LDT];
 
@@ -77,13 +73,11 @@ __global__ void __launch_bounds__(256, BLOCKED ? 1 : 2) gemm_tn_kernel(GemmArgs 
   };
 
   u64 acc[8][4];
-  u64 tot[BLOCKED ? 8 : 1][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       acc[i][j] = 0ull;
-      if (BLOCKED) tot[i][j] = 0ull;
     }
 
   const int nk = K / BK;
@@ -107,24 +101,9 @@ __global__ void __launch_bounds__(256, BLOCKED ? 1 : 2) gemm_tn_kernel(GemmArgs 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma2(a[i], b[j], acc[i][j]);
     }
-    if (BLOCKED) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tot[i][j] = add2(tot[i][j], acc[i][j]);
-          acc[i][j] = 0ull;
-        }
-    }
     if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
     buf ^= 1;
-  }
-  if (BLOCKED) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j];
   }
 
   // ---- epilogue
@@ -183,8 +162,7 @@ cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches) {
     return cudaErrorInvalidValue;
   const int64_t tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
   if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-  if (g.blocked_sum) gemm_tn_kernel<true><<<(unsigned)tiles, 256, 0, s>>>(g);
-  else gemm_tn_kernel<false><<<(unsigned)tiles, 256, 0, s>>>(g);
+  gemm_tn_kernel<<<(unsigned)tiles, 256, 0, s>>>(g);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -1111,11 +1111,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
 
   // CTA-pair kernel by default (4-7 % faster than the single-CTA one at config 2 once its cross-CTA barriers
   // stopped using cluster-scope acquire / release, which ptxas turns into CCTL.IVALL + MEMBAR.GPU);
-  // VASR_GEMM=tc1 selects the single-CTA kernel
-  static const bool use_pair = [] { const char* e = getenv("VASR_GEMM"); return !(e && strcmp(e, "tc1") == 0); }();
+  // the single-CTA kernel serves devices with one SM (and VASR_TC_PAIR=0 in a -DVASR_DEBUG build)
+  static const bool use_pair = debug_env_int("VASR_TC_PAIR", 1) != 0;
   const bool pair = use_pair && num_sms >= 2;
   // 192-column tiles (PairCfg<192>).  VASR_TC_T192=0 turns them off.
-  static const int t192_env = [] { const char* e = getenv("VASR_TC_T192"); return e ? atoi(e) : 1; }();
+  static const int t192_env = debug_env_int("VASR_TC_T192", 1);
   // Rule: 192-column tiles whenever N tiles into them without a tile narrower than 128 columns (192, 384, 512 =
   // 192 + 192 + 128, 576, 768, ...): a 128-column tile is exactly as fast as the control path (768 clocks of MMAs
   // per k-block against ~770), a 192-column one has 50 % more tensor work per k-block and per A tile loaded and
@@ -1152,11 +1152,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
   a.trace = g_trace;
-  static const int rot_env = [] { const char* e = getenv("VASR_TC_ROT"); return e ? atoi(e) : 1; }();
+  static const int rot_env = debug_env_int("VASR_TC_ROT", 1);
   a.rotate_n = rot_env;
-  static const int dbg_env = [] { const char* e = getenv("VASR_TC_DBG"); return e ? atoi(e) : 0; }();
+  static const int dbg_env = debug_env_int("VASR_TC_DBG", 0);
   a.dbg = dbg_env;
-  static const int pf_env = [] { const char* e = getenv("VASR_TC_PREFETCH"); return e ? atoi(e) : 0; }();   // measured: no gain
+  static const int pf_env = debug_env_int("VASR_TC_PREFETCH", 0);   // measured: no gain
   a.prefetch = pf_env;
 
   const int64_t tiles = (int64_t)a.n_tiles * a.m_tiles_per_batch * nb;
@@ -1165,7 +1165,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   const unsigned grid = (unsigned)((tiles < units ? tiles : units) * (pair ? 2 : 1));
   // W resident (see TcArgs::wres): the k-blocks must tile the stage ring, every n-tile needs a pair, and each
   // pair should see enough m-tiles to amortise its private copy of W.  VASR_TC_WRES=0 turns it off.
-  static const int wres_env = [] { const char* e = getenv("VASR_TC_WRES"); return e ? atoi(e) : 1; }();
+  static const int wres_env = debug_env_int("VASR_TC_WRES", 1);
   a.wres = 0;
   if (pair && wres_env) {
     const int64_t nkb = (g.K + TBK - 1) / TBK, per = units / a.n_tiles, m_tiles = (int64_t)a.m_tiles_per_batch * nb;

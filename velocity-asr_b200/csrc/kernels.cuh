@@ -34,8 +34,9 @@ struct GemmArgs {
   const float* pe_freq = nullptr;  // (N - pe_half)
   int pe_half = 0;
   int64_t pe_rows = 0;
-  int blocked_sum = 0;             // two-level summation over k tiles (used by the DFT rows)
 };
+// CUDA-core fp32 kernel behind vasr_linear (a general-purpose op for views the tensor-core kernel cannot take,
+// e.g. K % 4 != 0); the model's launch sequence never uses it.
 cudaError_t launch_gemm(const GemmArgs& g, cudaStream_t s, int64_t* launches);
 // tcgen05 / TMEM / TMA path with 3xTF32 split accumulation (gemm_tc.cu); needs g.W_split.  Returns
 // cudaErrorNotSupported when a tensor map cannot be encoded for this view.
@@ -100,18 +101,6 @@ cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B
 // per (b, j): mean and 1/(unbiased std + 1e-10) over the T frames, from the partials above.
 cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
                                      cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr);
-// xp[b, i] = pcm[b, reflect(i - pad)], i in [0, S + 2 pad); row stride ldp.
-cudaError_t launch_reflect_pad(const float* pcm, float* xp, int64_t B, int64_t S, int pad, int64_t ldp,
-                               cudaStream_t s, int64_t* launches);
-// spec (M, 2*nf): [re(0..nf) | im(0..nf)] -> raw[m, j] = log(sum_k fb[j,k] (re^2+im^2) + 1e-10).
-// fb is given band-sparse: for mel bin j, weights fb_w[fb_off[j] .. fb_off[j+1]) apply to
-// frequency bins fb_lo[j] ...
-cudaError_t launch_mel_log(const float* spec, int64_t lds, float* raw, int64_t M, int nf, int n_mels,
-                           const int* fb_lo, const int* fb_off, const float* fb_w, cudaStream_t s,
-                           int64_t* launches);
-// per (b, j): mean and 1/(unbiased std + 1e-10) over T frames of raw (B, T, n_mels).
-cudaError_t launch_mel_stats(const float* raw, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
-                             cudaStream_t s, int64_t* launches);
 // out[b, t + front, j] = (raw[b,t,j] - mean[b,j]) * rstd[b,j]  (mean == NULL: plain copy);
 // out has frames_per_utt rows per utterance; rows outside [front, front + T) are zeroed.
 cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* rstd, float* out, int64_t B,

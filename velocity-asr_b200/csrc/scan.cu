@@ -664,7 +664,7 @@ cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
   return e;
 }
 
-// picks the CTA shape: rows per CTA must divide Di.  VASR_SCAN_RPL=1|2|3 overrides rows per lane.
+// picks the CTA shape: rows per CTA must divide Di.  (-DVASR_DEBUG builds: VASR_SCAN_RPL=1|2|3 overrides rows per lane.)
 template <int LPR>
 cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
   constexpr int G = 32 / LPR;
@@ -673,9 +673,9 @@ cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
   if ((a.ldx & 3) || (a.lddt & 3) || (a.ldy & 1) || !al16(a.x) || !al16(a.dt) || (a.z && ((a.ldz & 3) || !al16(a.z))) ||
       (reinterpret_cast<uintptr_t>(a.y) & 7))
     return cudaErrorInvalidValue;
-  static const int rpl_env = [] { const char* e = getenv("VASR_SCAN_RPL"); return e ? atoi(e) : 0; }();
+  static const int rpl_env = debug_env_int("VASR_SCAN_RPL", 0);
   const int rpl = rpl_env >= 1 && rpl_env <= 3 ? rpl_env : 2;
-  static const int warps_env = [] { const char* e = getenv("VASR_SCAN_WARPS"); return e ? atoi(e) : 0; }();
+  static const int warps_env = debug_env_int("VASR_SCAN_WARPS", 0);
   if constexpr (LPR == 4) {
     if (rpl == 3 && a.Di % (4 * G * 3) == 0) return launch_seq<LPR, 4, 3>(a, s);
   }

@@ -98,6 +98,15 @@ def check(code: int):
         raise _EXC.get(code, RuntimeError)(f"libvasr: {msg}")
 
 
+def default_cuda_device():
+    """The CUDA device host-resident inputs are staged to when neither the input nor the model names one
+    (the process's current device).  Raises when there is none: this build has no CPU path."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("velocity_asr (B200 build): no CUDA device is available and there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def ptr(t):
     """Device (or host) address of a contiguous float32/int32 tensor, or None."""
     return None if t is None else c_void_p(t.data_ptr())

@@ -34,15 +34,18 @@ def frontend_tables(n_mels: int = N_MELS) -> Tuple[torch.Tensor, torch.Tensor]:
 def compute_mel_spectrogram(audio: torch.Tensor, sample_rate: int = SAMPLE_RATE, n_fft: int = N_FFT,
                             hop_length: int = HOP_LENGTH, n_mels: int = N_MELS,
                             normalize: bool = True) -> torch.Tensor:
-    """audio (S,) | (B, S) on a CUDA device -> (T, n_mels) | (B, T, n_mels), T = 1 + S // hop.
+    """audio (S,) | (B, S) -> (T, n_mels) | (B, T, n_mels), T = 1 + S // hop, on the device of `audio`.
 
     Same signature and result as audio.py:65-143.  The kernels are built for the model's
-    front end (16 kHz, 400-point DFT, hop 160); other values raise NotImplementedError."""
+    front end (16 kHz, 400-point DFT, hop 160); other values raise NotImplementedError.
+    The arithmetic always runs in the CUDA kernels: a CPU tensor (what scripts/transcribe.py:69 passes) is
+    copied to the current CUDA device, the result is copied back — a host copy around the same kernels, not
+    a CPU implementation; without a CUDA device the call raises."""
     if (sample_rate, n_fft, hop_length) != (SAMPLE_RATE, N_FFT, HOP_LENGTH):
         raise NotImplementedError("libvasr front end is fixed at sample_rate=16000, n_fft=400, hop_length=160")
-    if audio.device.type != "cuda":
-        raise RuntimeError("velocity_asr (B200 build) computes the mel spectrogram on CUDA only; "
-                           "move the audio to a CUDA device (no CPU fallback)")
+    home = audio.device
+    if home.type != "cuda":
+        audio = audio.to(_native.default_cuda_device())
     squeeze = audio.dim() == 1
     if squeeze:
         audio = audio.unsqueeze(0)
@@ -55,7 +58,8 @@ def compute_mel_spectrogram(audio: torch.Tensor, sample_rate: int = SAMPLE_RATE,
         _native.check(eng.lib.vasr_log_mel(eng.handle, _native.ptr(pcm), B, S, int(bool(normalize)),
                                            _native.ptr(mel),
                                            ctypes.c_void_p(torch.cuda.current_stream(pcm.device).cuda_stream)))
-    return mel.squeeze(0) if squeeze else mel
+    mel = mel.squeeze(0) if squeeze else mel
+    return mel if home.type == "cuda" else mel.to(home)
 
 
 _MEL_ENGINES = {}
@@ -64,7 +68,7 @@ _MEL_ENGINES = {}
 def _mel_engine(device: torch.device, n_mels: int):
     """A weight-less handle that only carries the front-end tables."""
     from .config import VelocityASRConfig
-    from .engine import _Engine
+    from .model import _Engine
     idx = device.index if device.index is not None else torch.cuda.current_device()
     key = (idx, n_mels)
     eng = _MEL_ENGINES.get(key)

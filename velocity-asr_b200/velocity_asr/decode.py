@@ -13,12 +13,13 @@ BLANK_TOKEN = 0  # decode.py:14
 
 def ctc_greedy_decode(logits: torch.Tensor, blank_token: int = BLANK_TOKEN,
                       collapse_repeated: bool = True) -> List[List[int]]:
-    """logits (B, L, V) on a CUDA device -> token-id lists.  Same rule as decode.py:46-69:
-    argmax (ties -> lowest index), drop blanks, collapse repeats, a blank resets the repeat state."""
+    """logits (B, L, V) -> token-id lists.  Same rule as decode.py:46-69: argmax (ties -> lowest index),
+    drop blanks, collapse repeats, a blank resets the repeat state.  Runs in the CUDA kernels whatever the
+    device of `logits` (CPU logits are copied to the current CUDA device first; no CUDA device -> RuntimeError)."""
     if logits.dim() != 3:
         raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
-    if logits.device.type != "cuda":
-        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    if logits.device.type != "cuda":       # host logits: staged to the current CUDA device (no CPU decoder exists)
+        logits = logits.to(_native.default_cuda_device())
     B, L, V = logits.shape
     if B == 0:
         return []
@@ -43,8 +44,8 @@ def ctc_greedy_decode_with_timestamps(logits: torch.Tensor, blank_token: int = B
     frame * 2 * 160 / 16000 (scripts/transcribe.py:42-45)."""
     if logits.dim() != 3:
         raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
-    if logits.device.type != "cuda":
-        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    if logits.device.type != "cuda":       # host logits: staged to the current CUDA device (no CPU decoder exists)
+        logits = logits.to(_native.default_cuda_device())
     B, L, V = logits.shape
     if B == 0:
         return []
@@ -61,6 +62,39 @@ def ctc_greedy_decode_with_timestamps(logits: torch.Tensor, blank_token: int = B
     buf, lens = buf.cpu().numpy(), lens.cpu().tolist()
     return [(buf[0, b, :n].tolist(), list(zip(buf[1, b, :n].tolist(), buf[2, b, :n].tolist())))
             for b, n in enumerate(lens)]
+
+
+def frames_to_seconds(frame_idx: int, hop_length: int = 160, sample_rate: int = 16000) -> float:
+    """Token index -> seconds (scripts/transcribe.py:42-45): one token spans two mel frames (stride-2 conv)."""
+    return (frame_idx * 2 * hop_length) / sample_rate
+
+
+def words_with_timestamps(tokens: List[int], timestamps: List[Tuple[int, int]], vocabulary: List[str]
+                          ) -> List[dict]:
+    """Word assembly of scripts/transcribe.py:80-126 on one utterance's output of
+    ctc_greedy_decode_with_timestamps: characters accumulate into a word until a space / subword marker; a
+    word starts at its first character's start frame and ends at the END frame of the separator that closed
+    it (the last word: at the end frame of the last token).  Returns [{"word", "start", "end"}] in seconds."""
+    words, chars, start = [], [], None
+
+    def close(end_frame):
+        text = "".join(chars).replace("▁", "")
+        if text:
+            words.append({"word": text, "start": frames_to_seconds(start), "end": frames_to_seconds(end_frame)})
+
+    for tok, (f0, f1) in zip(tokens, timestamps):
+        ch = vocabulary[tok] if 0 <= tok < len(vocabulary) else "<unk>"
+        if ch in (" ", "▁"):
+            if chars:
+                close(f1)
+                chars, start = [], None
+        else:
+            if start is None:
+                start = f0
+            chars.append(ch)
+    if chars and timestamps:
+        close(timestamps[-1][1])
+    return words
 
 
 @dataclass
@@ -84,8 +118,8 @@ def ctc_beam_search(logits: torch.Tensor, beam_width: int = 10, blank_token: int
                                   "Python lm_scorer")
     if logits.dim() != 3:
         raise RuntimeError(f"expected (batch, seq_len, vocab) logits, got {tuple(logits.shape)}")
-    if logits.device.type != "cuda":
-        raise RuntimeError("velocity_asr (B200 build) decodes on CUDA only (no CPU fallback)")
+    if logits.device.type != "cuda":       # host logits: staged to the current CUDA device (no CPU decoder exists)
+        logits = logits.to(_native.default_cuda_device())
     B, L, V = logits.shape
     W = int(beam_width)
     if B == 0:

@@ -5,6 +5,7 @@ import ctypes
 import os
 from typing import Dict, Iterable, Iterator, List, Optional, Tuple, Union
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -19,8 +20,14 @@ def _stream_ptr(device) -> ctypes.c_void_p:
 
 def _token_lists(tokens: torch.Tensor, lens: torch.Tensor) -> List[List[int]]:
     """(B, L) left-packed int32 ids + (B,) counts (host tensors) -> ragged Python lists."""
-    tok = tokens.numpy()
-    return [tok[b, :n].tolist() for b, n in enumerate(lens.tolist())]
+    tok, counts = tokens.numpy(), lens.numpy()
+    # one boolean gather + one tolist for the whole batch, then list slices (no per-utterance numpy calls)
+    flat = tok[np.arange(tok.shape[1])[None, :] < counts[:, None]].tolist()
+    out, o = [], 0
+    for n in counts.tolist():
+        out.append(flat[o:o + n])
+        o += n
+    return out
 
 
 def _lengths_tensor(lengths, B: int) -> torch.Tensor:
@@ -34,8 +41,17 @@ def _lengths_tensor(lengths, B: int) -> torch.Tensor:
 class _Engine:
     """Owns one vasr_handle (one GPU).  Re-uploads weights when the parameters change."""
 
+    @staticmethod
+    def config_key(cfg: VelocityASRConfig) -> tuple:
+        """The config fields the native handle is created from: a change of any of them (e.g. scan_mode
+        edited after the first call) makes VELOCITYASR._engine build a new handle."""
+        return (cfg.mel_bins, cfg.d_model, cfg.ssm_layers, cfg.ssm_state_dim, cfg.ssm_expand_ratio,
+                cfg.ssm_kernel_size, cfg.global_ssm_layers, cfg.global_ssm_state_dim, cfg.attention_heads,
+                cfg.attention_dim, cfg.vocab_size, cfg.scan_mode)
+
     def __init__(self, cfg: VelocityASRConfig, device: torch.device):
         self.device = device
+        self.cfg_key = self.config_key(cfg)
         self.lib = _native.lib()
         c = _native.VasrConfig(
             cfg.mel_bins, cfg.d_model, cfg.ssm_layers, cfg.ssm_state_dim, cfg.ssm_expand_ratio,
@@ -58,7 +74,12 @@ class _Engine:
 
     def sync_weights(self, state: Dict[str, torch.Tensor], extra: Dict[str, torch.Tensor], quantized: bool = False,
                      act_qparams: Optional[Dict[str, Tuple[float, float]]] = None):
-        fp = (quantized,) + tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
+        # Fingerprint = identity, in-place version counter and shape of every tensor, plus what else shapes
+        # the committed weights.  Contract: edits that bypass the version counter (p.data.copy_(), .data.mul_(),
+        # EMA updates through .data) are NOT seen — call VELOCITYASR.refresh_weights() after such an edit.
+        qp = tuple(sorted((act_qparams or {}).items())) if quantized else ()
+        fp = (quantized, qp) + tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
+        fp += tuple((k, v.data_ptr(), v._version) for k, v in extra.items())
         if fp == self.fingerprint:
             return
         _native.check(self.lib.vasr_set_quantization(self.handle, int(quantized)))
@@ -77,7 +98,10 @@ class VELOCITYASR(nn.Module):
     count_parameters; plus transcribe(audio) for the fused PCM -> tokens path.
 
     Inference only (the reference's callers run it under eval() + no_grad(),
-    scripts/transcribe.py:76,225); dropout is the identity.  CUDA only: there is no CPU path.
+    scripts/transcribe.py:76,225); dropout is the identity.  All arithmetic runs in the CUDA kernels: there is
+    no CPU path.  Host tensors are accepted the way the reference's own scripts pass them (test_vel.py:24-37
+    never moves model or input off the CPU): they are copied to a CUDA device (the model's, else the current
+    one), the kernels run there, and the result is copied back to the input's device.
     """
 
     def __init__(self, config: Optional[VelocityASRConfig] = None):
@@ -95,20 +119,34 @@ class VELOCITYASR(nn.Module):
     def _device(self) -> torch.device:
         return self.temporal_binding.conv.weight.device
 
+    def _exec_device(self, like: Optional[torch.Tensor] = None) -> torch.device:
+        """Where the kernels run: the input's CUDA device, else the model's, else the current CUDA device."""
+        if like is not None and like.device.type == "cuda":
+            return like.device
+        dev = self._device()
+        return dev if dev.type == "cuda" else _native.default_cuda_device()
+
+    def refresh_weights(self) -> None:
+        """Forget the device copies of the weights: the next call re-uploads them.  Needed only after edits
+        that bypass torch's version counter (p.data.copy_(), .data.mul_(), EMA through .data)."""
+        for eng in self._engines.values():
+            eng.fingerprint = None
+
     def _engine(self, device: torch.device) -> _Engine:
         if device.type != "cuda":
-            raise RuntimeError(
-                "velocity_asr (B200 build) runs on CUDA only: move the model and its input to a "
-                "CUDA device (model.to('cuda')); there is no CPU fallback")
+            device = self._exec_device()
         if self.config.scan_mode not in SCAN_MODES:
             raise ValueError(f"Unknown scan_mode: {self.config.scan_mode}")
         idx = device.index if device.index is not None else torch.cuda.current_device()
         device = torch.device("cuda", idx)
         eng = self._engines.get(idx)
+        if eng is not None and eng.cfg_key != _Engine.config_key(self.config):
+            eng.close()                     # the config changed under the handle (e.g. scan_mode): rebuild it
+            eng = None
         if eng is None:
             eng = _Engine(self.config, device)
             self._engines[idx] = eng
-        from .frontend import frontend_tables
+        from .audio import frontend_tables
         fb, win = frontend_tables(self.config.mel_bins)
         # same keys and order as state_dict(), without the detach/copy work of building one per call
         state = dict(self.named_parameters())
@@ -128,9 +166,10 @@ class VELOCITYASR(nn.Module):
         if not isinstance(x, torch.Tensor):
             raise TypeError(f"{what} must be a torch.Tensor")
         dev = self._device()
-        if x.device != dev and not (x.device.type == "cuda" and dev.type == "cuda" and
-                                    (x.device.index or 0) == (dev.index or 0)):
+        if x.device.type == "cuda" and dev.type == "cuda" and (x.device.index or 0) != (dev.index or 0):
             raise RuntimeError(f"{what} is on {x.device} but the model is on {dev}")
+        if x.device.type != "cuda":         # host input: staged to the execution device (see the class docstring)
+            x = x.to(self._exec_device())
         return x.to(torch.float32).contiguous()
 
     # ---- reference API ----------------------------------------------------------------------
@@ -141,7 +180,9 @@ class VELOCITYASR(nn.Module):
         `lengths` (B frame counts; not in the reference, whose collator pads and never masks): utterance b
         has lengths[b] valid frames and its logits rows [: get_output_length(lengths[b])] equal those of
         forward(mel[b:b+1, :lengths[b]]); rows past that are padding."""
+        home = mel_spectrogram.device if isinstance(mel_spectrogram, torch.Tensor) else None
         mel = self._check_input(mel_spectrogram, "mel_spectrogram")
+        back = (lambda t: t) if home is None or home.type == "cuda" else (lambda t: t.to(home))
         if mel.dim() != 3 or mel.size(2) != self.config.mel_bins:
             raise RuntimeError(f"expected (batch, frames, {self.config.mel_bins}) input, got {tuple(mel.shape)}")
         eng = self._engine(mel.device)
@@ -155,7 +196,7 @@ class VELOCITYASR(nn.Module):
             if B > 0 and T > 0:
                 _native.check(eng.lib.vasr_forward_ragged(eng.handle, _native.ptr(mel), _native.ptr(lens), B, T,
                                                           _native.ptr(logits), _stream_ptr(mel.device)))
-            return logits
+            return back(logits)
         feats = None
         if return_features:
             feats = {k: torch.empty(B, L, self.config.d_model, device=mel.device, dtype=torch.float32)
@@ -166,7 +207,9 @@ class VELOCITYASR(nn.Module):
                 _native.ptr(feats["temporal_binding"]) if feats else None,
                 _native.ptr(feats["local_features"]) if feats else None,
                 _native.ptr(feats["fused_features"]) if feats else None, _stream_ptr(mel.device)))
-        return (logits, feats) if return_features else logits
+        if return_features:
+            return back(logits), {k: back(v) for k, v in feats.items()}
+        return back(logits)
 
     def get_output_length(self, input_length: int) -> int:
         """model.py:370-383"""
@@ -184,7 +227,7 @@ class VELOCITYASR(nn.Module):
         if audio.dim() == 1:
             audio = audio.unsqueeze(0)
         B, S = audio.shape
-        dev = self._device()
+        dev = self._exec_device(audio)
         eng = self._engine(dev)
         L = self.get_output_length(1 + S // 160)
         slen = None if lengths is None else _lengths_tensor(lengths, B)
@@ -221,7 +264,7 @@ class VELOCITYASR(nn.Module):
         are identical to calling transcribe() on each batch.  Batches are (B, S) float32 CPU
         tensors (pin them for full PCIe speed); shapes may change from batch to batch.  An item may also
         be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths)."""
-        dev = self._device()
+        dev = self._exec_device()
         eng = self._engine(dev)
         comp = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
@@ -289,7 +332,7 @@ class VELOCITYASR(nn.Module):
             if u.dim() != 1:
                 raise RuntimeError("transcribe_list takes 1-D PCM tensors")
         order = sorted(range(len(utterances)), key=lambda i: int(utterances[i].numel()))
-        dev = self._device()
+        dev = self._exec_device()
         for j in range(0, len(order), max_batch):
             part = order[j:j + max_batch]
             lens = [int(utterances[i].numel()) for i in part]
