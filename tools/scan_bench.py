@@ -33,6 +33,12 @@ def run(B=64, L=751, Di=384, N=64, mode="sequential", structured=True, gate=True
 
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
+    if "--B" in sys.argv:        # batch sweep: --B 49 64 74 ...
+        i = sys.argv.index("--B")
+        mode = "parallel" if "--quirk" in sys.argv else "sequential"
+        for b in sys.argv[i + 1:]:
+            print(json.dumps(run(B=int(b), mode=mode, iters=10)), flush=True)
+        sys.exit(0)
     if "--quirk" in sys.argv:
         cases = [dict(mode="parallel", N=32, L=93), dict(mode="parallel")]
     else:
