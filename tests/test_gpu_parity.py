@@ -240,6 +240,35 @@ def test_scan_scaled_state_extremes(va):
     assert np.abs(got[1][:, zero_rows]).max() < 1e-9            # y = 0 (up to the 1e-12 clamp) where x is 0 throughout
 
 
+@pytest.mark.parametrize("B,L", [(64, 130), (50, 20), (50, 16), (75, 49), (150, 33)])
+def test_scan_large_batch_time_split(va, B, L):
+    """The large-batch kernel (row pairs per packed register, time axis cut into slots that hand the state over
+    through global memory; scan.cu, scan_rp_kernel) against the oracle: shapes where a slot holds a fraction of a
+    chain (64 x 130: 5.8 chunks of 9 per slot), about one chunk (50 x 20), whole chains only (50 x 16: no
+    hand-over) or several chains plus two fractions (150 x 33), with the extremes of test_scan_scaled_state_extremes
+    placed across the cuts."""
+    Di, N = 384, 64
+    x, dt, A, Bm, Cm, D = FU.scan_inputs(B, L, Di, N, seed=500 + B + L, structured_a=True)
+    x[:, 3:9, :64] = 0.0
+    x[:, 14:18, 64:128] *= 1e-25                                # straddles the first chunk boundary
+    x[:, min(L - 1, 30):min(L, 35), 128:192] *= 1e4
+    rs = np.random.RandomState(B)
+    z = rs.standard_normal(x.shape).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    got = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="sequential")
+    again = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="sequential")
+    assert torch.equal(got, again)                             # the hand-over order does not touch the arithmetic
+    d = lambda a: a.astype(np.float64)
+    ref = O.scan_sequential(d(x), d(dt), d(A), d(Bm), d(Cm), d(D)) * O.silu(d(z))
+    got = got.cpu().numpy()
+    assert np.isfinite(got).all()
+    scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-6
+    assert (np.abs(got - ref) / scale).max() < 1e-4
+    # an utterance alone (small-batch kernel, no split) gives the same numbers to fp32 rounding
+    alone = va.selective_scan(t(x[:1]), t(dt[:1]), t(A), t(Bm[:1]), t(Cm[:1]), t(D), z=t(z[:1]), scan_mode="sequential")
+    assert (np.abs(alone.cpu().numpy() - got[:1]) / scale[:1]).max() < 2e-5
+
+
 def test_scan_mamba_signature(va):
     x, dt, A, Bm, Cm, D = FU.scan_inputs(2, 50, 384, 64, 77, True)
     t = lambda a: torch.from_numpy(a).cuda()

@@ -27,9 +27,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True: libvasr_dbg.so with -DVASR_DEBUG (the tuning switches of common.cuh's debug_env_int read the
+    environment); load it with VASR_LIB=<path> for A/B runs on one GPU box.  The shipped library has none of them."""
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_dbg" if debug else "build")
+    target = OUT.replace("libvasr.so", "libvasr_dbg.so") if debug else OUT
+    flags = FLAGS + (["-DVASR_DEBUG"] if debug else [])
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vasr.h"))
@@ -39,7 +43,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -49,11 +53,11 @@ def build(force=False, verbose=False):
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static"]
+    if force or procs or _stale(target, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", target] + objs + ["-cudart", "static"]
         subprocess.check_call(cmd)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -562,6 +562,7 @@ int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t 
   a.B = B; a.L = L; a.Di = di; a.N = w.N;
   a.parallel_quirk = quirk;
   a.structured_a = w.structured;
+  a.num_sms = h->num_sms;
   const bool t = h->timing && h->ev_used + 2 <= (int)h->ev.size();
   if (t) cudaEventRecord(h->ev[h->ev_used], s);
   KL(launch_selective_scan(a, s, &h->launches));
@@ -1044,7 +1045,11 @@ int vasr_selective_scan(const float* x, int64_t ldx, const float* dt, int64_t ld
   a.B = B; a.L = L; a.Di = (int)Di; a.N = (int)N;
   a.parallel_quirk = scan_mode == VASR_SCAN_PARALLEL;
   a.structured_a = structured;
-  KL(launch_selective_scan(a, static_cast<cudaStream_t>(stream), nullptr));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&a.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  KL(launch_selective_scan(a, s, nullptr));
   return VASR_OK;
 }
 

@@ -78,6 +78,7 @@ struct ScanArgs {
   int Di = 0, N = 0;
   int parallel_quirk = 0;     // 0: true recurrence (sequential/mamba); 1: reference 'parallel'
   int structured_a = 0;       // A[n] == -(n+1): powers of exp(-dt) instead of one exp per state
+  int num_sms = 0;            // 0 -> 148
 };
 cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* launches);
 

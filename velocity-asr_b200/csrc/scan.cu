@@ -26,6 +26,9 @@
 //     hP[0] = 0;  hP[t] = hP[parent] + exp(A S[t]) * (H[t] - exp(A (S[t]-S[parent])) H[parent])
 // which is evaluated left to right with O(log L) saved ancestors per state.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -648,6 +651,541 @@ __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 :
   finalize();
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-packed recurrence kernel: the true recurrence for structured A and N = 64 (every shape the model runs).
+//
+// What was measured on scan_seq_kernel at batch 64 (ncu: profiles/scan_ncu.json; batch sweep: tools/scan_bench.py):
+// every lane needs the 16 B and 16 C values of its states in registers each step, for only two rows — 4 KB per
+// warp-step through the 128 B/clk shared-memory -> register path (41 wavefronts per warp-step, 69 % of the LSU data
+// pipe); a third of the FMA-pipe time goes to scalar set-up arithmetic; and 384 CTAs over 148 SMs leave 3 CTAs on
+// the critical SMs against 2.59 on average (0.20 ms at 2 CTAs per SM, 0.27 ms at 3: the time is a step function
+// of the CTAs on the fullest SM).  This kernel changes all three:
+//   * a packed fp32x2 register holds the SAME state of TWO ROWS (a row pair), not two states of one row.  B[n] and
+//     C[n] then enter the FFMA2 as scalar-broadcast operands (SASS `.F32`, addend and multiplicand alike), so one
+//     16-byte load of B feeds 2 * RP rows; with RP = 2 row pairs per lane (4 rows, 64 state registers) the B / C
+//     traffic per row halves (10.5 LDS.128 per 32-row warp-step);
+//   * all per-row set-up (exponent arguments, u = x dt, the ratio of consecutive scales, the power seeds) runs as
+//     packed operations on the pair;
+//   * the time axis is cut at chunk boundaries and dealt out evenly: the grid is a fixed number of slots
+//     (resident CTAs), slot s owns the range [s T / S, (s + 1) T / S) of the chunk sequence of all chains laid end
+//     to end (a chain = the rows of one CTA x the whole utterance).  A slot first runs the pieces that start a chain
+//     (no dependency), last the tail of the chain its range begins in, which continues from the state the previous
+//     slot published (state + carried scale through global memory, one flag per slot).  The split changes no
+//     arithmetic: a row sees exactly the operation sequence of the unsplit recurrence, whatever the CTA shape.
+// Everything else follows scan_seq_kernel: cp.async tiles in natural layout three stages deep, operands and set-up
+// one step ahead, state carried divided by the input, transpose-reduce of four steps across the four lanes of a
+// row group one block late, D skip + silu(z) gate + 16-byte store by the lane that ends up with a finished value.
+//
+// What it bought, and what bounds it now (same box, 64 / 128 / 512 x 751 x 384): 0.252 / 0.420 / 1.57 ms against
+// 0.268 / 0.498 / 1.64 ms.  184.75 instructions per 32-row warp-step (116 packed; scan_seq_kernel: 124.5 per 16
+// rows, 48 packed), LSU data pipe 49 %, FMA pipe 62 %, XU 39 % at two warps per sub-partition: no pipe saturates.
+// A fit over both kernels prices a packed instruction at ~2.8 clocks and any other at ~1.2, i.e. the three packed
+// operations per state and step (47 per 16 rows: ~130 clocks) are two thirds of the time, and a warp alone on its
+// sub-partition issues in 45 % of the cycles (37 % fixed-latency waits of the in-order pipe).  A third CTA per SM
+// (168 registers, two tile stages) and a fully unrolled 16-step body (48 KB of code: instruction-cache misses were
+// the top stall) were both slower.  At batch 64 the floor is the chain itself: 751 sequential steps at the pace
+// of a sub-partition that two warps share.
+// ------------------------------------------------------------------------------------------
+struct SplitArgs {
+  u64* state = nullptr;           // per slot: THREADS * (RP * 17) packed values (RP * 16 states + RP carried scales)
+  unsigned int* flags = nullptr;  // per slot: launch epoch once the slot's state is published
+  unsigned int epoch = 0;
+  int n_slots = 0;
+};
+
+__device__ __forceinline__ u64 shfl_xor2(u64 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int RP, int WARPS, int OCC>   // OCC: CTAs per SM the register budget is cut for
+__global__ void __launch_bounds__(WARPS * 32, OCC) scan_rp_kernel(ScanArgs a, SplitArgs sa) {
+  pdl_wait();
+  constexpr int N = 64, G = 8, R = 2 * RP;      // 4 lanes per row group, G groups per warp, R rows per lane
+  constexpr int ROWS = WARPS * G * R;
+  constexpr int THREADS = WARPS * 32;
+  constexpr int LDR = ROWS + 8;                 // row stride of the x / dt / z tiles: the finalising lanes of a group
+                                                // read four different timesteps, 8 floats of padding keep them apart
+  constexpr int NF = N / 4, RF = ROWS / 4;
+  constexpr int STAGE_FLOATS = TCH * (2 * N + 3 * LDR);
+  constexpr int NST = 3;                        // tile stages: chunk c in use, c + 1 landed, c + 2 in flight
+  constexpr int NV = 4 * RP;                    // packed partials per lane per block of four steps
+  constexpr int SW = RP * 17;                   // packed values per thread in a published state
+
+  extern __shared__ __align__(16) float scan_smem[];
+  auto sB = [&](int st) { return scan_smem + st * STAGE_FLOATS; };
+  auto sC = [&](int st) { return scan_smem + st * STAGE_FLOATS + TCH * N; };
+  auto sX = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N; };
+  auto sDt = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N + TCH * LDR; };
+  auto sZ = [&](int st) { return scan_smem + st * STAGE_FLOATS + 2 * TCH * N + 2 * TCH * LDR; };
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, j = lane & 3;
+  const int rl0 = (warp * G + g) * R;
+  const int64_t L = a.L;
+  const bool gate = a.z != nullptr;
+  const int tiles = a.Di / ROWS;
+  const int64_t cpc = (L + TCH - 1) / TCH;                  // chunks per chain
+  const int64_t n_chains = a.B * tiles;
+
+  // this slot's range of the chunk sequence of all chains laid end to end
+  int64_t f0, f1;
+  if (sa.n_slots > 0) {
+    const int64_t total = n_chains * cpc;
+    f0 = total * blockIdx.x / sa.n_slots;
+    f1 = total * (blockIdx.x + 1) / sa.n_slots;
+  } else {
+    f0 = (int64_t)blockIdx.x * cpc;
+    f1 = f0 + cpc;
+  }
+  if (f1 <= f0) {
+    pdl_trigger();
+    return;
+  }
+  const int64_t c_first = f0 / cpc, c_last = (f1 - 1) / cpc;
+
+  const u64 CR = bcast2(-LOG2E);                            // r  = exp(-dt)
+  const u64 CE = bcast2(-LOG2E * (float)(4 * j + 1));       // e  = r^(4j+1)
+  const u64 CQ = bcast2(-LOG2E * 16.0f);                    // rq = r^16: states 4 (j + 4 m) + i, m = 0..3
+
+  // pieces in descending chain order: the ones that start a chain first, the dependent tail last
+  for (int64_t chain = c_last; chain >= c_first; --chain) {
+    const int cb = (int)((f0 > chain * cpc ? f0 : chain * cpc) - chain * cpc);
+    const int ce = (int)((f1 < (chain + 1) * cpc ? f1 : (chain + 1) * cpc) - chain * cpc);
+    const bool load_state = cb > 0, save_state = ce < cpc;
+    const bool last_piece = chain == c_first;
+    const int64_t b = chain / tiles;
+    const int d0 = (int)(chain % tiles) * ROWS;
+
+    u64 DV[RP];
+#pragma unroll
+    for (int p = 0; p < RP; ++p)
+      DV[p] = a.D ? pack2(__ldg(a.D + d0 + rl0 + 2 * p), __ldg(a.D + d0 + rl0 + 2 * p + 1)) : 0ull;
+
+    const float* gB = a.Bm + b * L * a.ldb;
+    const float* gC = a.Cm + b * L * a.ldc;
+    const float* gX = a.x + b * L * a.ldx + d0;
+    const float* gDt = a.dt + b * L * a.lddt + d0;
+    const float* gZ = gate ? a.z + b * L * a.ldz + d0 : nullptr;
+    float* gY = a.y + b * L * a.ldy + d0 + rl0;
+
+    // Tile loads.  Thread tid moves, per chunk, the float4 pieces (t = tb + TSB i, f = tid % NF) of B and C and
+    // (t = tx + TSX i, f = tid % RF) of x / dt / z: fixed per-thread offsets, so a chunk costs one pointer advance
+    // per array and no index arithmetic (the first version recomputed every address from tid and re-read the
+    // strides from the constant bank: 345 instructions per chunk, 18 % of a lone warp's time).
+    constexpr int TSB = THREADS / NF, TSX = THREADS / RF;      // timesteps between a thread's pieces
+    static_assert(THREADS % NF == 0 && THREADS % RF == 0 && TCH % TSB == 0 && TCH % TSX == 0, "tile shape");
+    const int tb = tid / NF, fb = tid % NF, tx = tid / RF, fx = tid % RF;
+    const float* qB = gB + ((int64_t)cb * TCH + tb) * a.ldb + 4 * fb;
+    const float* qC = gC + ((int64_t)cb * TCH + tb) * a.ldc + 4 * fb;
+    const float* qX = gX + ((int64_t)cb * TCH + tx) * a.ldx + 4 * fx;
+    const float* qD = gDt + ((int64_t)cb * TCH + tx) * a.lddt + 4 * fx;
+    const float* qZ = gate ? gZ + ((int64_t)cb * TCH + tx) * a.ldz + 4 * fx : nullptr;
+    const int oB = tb * N + 4 * fb, oX = tx * LDR + 4 * fx;     // offsets inside a stage
+    int c_issue = cb;                                            // next chunk to be requested
+    auto issue = [&]() {               // always commits a group (an empty one past the piece's last chunk)
+      const int c = c_issue++;
+      if (c < ce) {
+        const int st = (c - cb) % NST;
+        float* dB = sB(st) + oB; float* dC = sC(st) + oB;
+        float* dX = sX(st) + oX; float* dD = sDt(st) + oX; float* dZ = sZ(st) + oX;
+        const int64_t left = L - (int64_t)c * TCH;               // timesteps this chunk holds
+        if (left >= TCH) {
+#pragma unroll
+          for (int i = 0; i < TCH / TSB; ++i) {
+            cp_async16(dB + i * TSB * N, qB + (int64_t)i * TSB * a.ldb);
+            cp_async16(dC + i * TSB * N, qC + (int64_t)i * TSB * a.ldc);
+          }
+#pragma unroll
+          for (int i = 0; i < TCH / TSX; ++i) {
+            cp_async16(dX + i * TSX * LDR, qX + (int64_t)i * TSX * a.ldx);
+            cp_async16(dD + i * TSX * LDR, qD + (int64_t)i * TSX * a.lddt);
+            if (gate) cp_async16(dZ + i * TSX * LDR, qZ + (int64_t)i * TSX * a.ldz);
+          }
+        } else {                                                 // the last chunk of a chain
+#pragma unroll
+          for (int i = 0; i < TCH / TSB; ++i)
+            if (tb + i * TSB < left) {
+              cp_async16(dB + i * TSB * N, qB + (int64_t)i * TSB * a.ldb);
+              cp_async16(dC + i * TSB * N, qC + (int64_t)i * TSB * a.ldc);
+            }
+#pragma unroll
+          for (int i = 0; i < TCH / TSX; ++i)
+            if (tx + i * TSX < left) {
+              cp_async16(dX + i * TSX * LDR, qX + (int64_t)i * TSX * a.ldx);
+              cp_async16(dD + i * TSX * LDR, qD + (int64_t)i * TSX * a.lddt);
+              if (gate) cp_async16(dZ + i * TSX * LDR, qZ + (int64_t)i * TSX * a.ldz);
+            }
+        }
+        qB += (int64_t)TCH * a.ldb; qC += (int64_t)TCH * a.ldc;
+        qX += (int64_t)TCH * a.ldx; qD += (int64_t)TCH * a.lddt;
+        if (gate) qZ += (int64_t)TCH * a.ldz;
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) issue();                // the tiles travel while the state is fetched
+
+    // ---- state: zero at the start of a chain, else what the previous slot published
+    u64 H[RP][16];
+    u64 s_carry[RP];
+    if (load_state) {
+      if (tid == 0) {
+        const volatile unsigned int* fl = sa.flags + (blockIdx.x - 1);
+        const unsigned long long t0 = global_ns();
+        while (*fl != sa.epoch) {
+          __nanosleep(100);
+          if (global_ns() - t0 > 4000000000ull) __trap();     // 4 s: a lost hand-over must not hang the device
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      const u64* st = sa.state + (size_t)(blockIdx.x - 1) * THREADS * SW + tid;
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) H[p][k] = __ldcg(st + (size_t)(p * 16 + k) * THREADS);
+        s_carry[p] = __ldcg(st + (size_t)(RP * 16 + p) * THREADS);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) H[p][k] = 0ull;
+        s_carry[p] = bcast2(1.0f);
+      }
+    }
+
+    // set-up of one step for one row pair, from its dt and x (packed over the two rows)
+    struct Pre {
+      u64 ER[RP], R1[RP], R2[RP], RQ[RP], S[RP];
+    };
+    struct Raw {       // MUFU results of a step's set-up, before they are combined
+      float r[R], e[R], q[R], u[R], inv[R];
+    };
+    auto load_dx = [&](u64 (&DT)[RP], u64 (&X)[RP], const float* pD, const float* pX, int t) {
+      if (RP == 2) {
+        const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(pD + t * LDR);
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(pX + t * LDR);
+        DT[0] = d.x; DT[RP - 1] = d.y; X[0] = x.x; X[RP - 1] = x.y;
+      } else {
+        DT[0] = *reinterpret_cast<const u64*>(pD + t * LDR);
+        X[0] = *reinterpret_cast<const u64*>(pX + t * LDR);
+      }
+    };
+    auto mufu_phase = [&](const u64 (&DT)[RP], const u64 (&X)[RP], Raw& w) {
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+        float a0, a1;
+        unpack2(mul2(DT[p], CR), a0, a1);
+        w.r[2 * p] = ex2_approx(a0); w.r[2 * p + 1] = ex2_approx(a1);
+        unpack2(mul2(DT[p], CE), a0, a1);
+        w.e[2 * p] = ex2_approx(a0); w.e[2 * p + 1] = ex2_approx(a1);
+        unpack2(mul2(DT[p], CQ), a0, a1);
+        w.q[2 * p] = ex2_approx(a0); w.q[2 * p + 1] = ex2_approx(a1);
+        unpack2(mul2(X[p], DT[p]), a0, a1);
+        if (fabsf(a0) < 1e-12f) a0 = copysignf(1e-12f, a0);
+        if (fabsf(a1) < 1e-12f) a1 = copysignf(1e-12f, a1);
+        w.u[2 * p] = a0; w.u[2 * p + 1] = a1;
+        w.inv[2 * p] = rcp_approx(a0); w.inv[2 * p + 1] = rcp_approx(a1);
+      }
+    };
+    auto pack_phase = [&](const Raw& w, const u64 (&s_prev)[RP], Pre& o) {
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+        const u64 ratio = mul2(s_prev[p], pack2(w.inv[2 * p], w.inv[2 * p + 1]));     // u_{t-1} / u_t
+        o.ER[p] = mul2(pack2(w.e[2 * p], w.e[2 * p + 1]), ratio);                     // r^(4j+1) u_{t-1} / u_t
+        o.R1[p] = pack2(w.r[2 * p], w.r[2 * p + 1]);
+        o.R2[p] = mul2(o.R1[p], o.R1[p]);
+        o.RQ[p] = pack2(w.q[2 * p], w.q[2 * p + 1]);
+        o.S[p] = pack2(w.u[2 * p], w.u[2 * p + 1]);
+      }
+    };
+
+    // finalisation (one block of four steps late): see scan_seq_kernel
+    u64 ypv[NV], FX[RP], FZ[RP];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ypv[i] = 0ull;
+#pragma unroll
+    for (int p = 0; p < RP; ++p) FX[p] = FZ[p] = 0ull;
+    float* fy = gY;
+    bool fvalid = false;
+    auto finalize = [&]() {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int lane_bit = 2 >> r;
+        const int cnt = (NV / 2) >> r;
+        const bool hi = (j & lane_bit) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const u64 mine = hi ? ypv[i + cnt] : ypv[i];
+          const u64 other = hi ? ypv[i] : ypv[i + cnt];
+          ypv[i] = add2(mine, shfl_xor2(other, lane_bit));
+        }
+      }
+      float out[R];
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+        u64 y = fma2(FX[p], DV[p], ypv[p]);
+        if (gate) {          // y * silu(z) = y * z / (1 + 2^(-z log2 e))
+          float e0, e1;
+          unpack2(mul2(FZ[p], CR), e0, e1);
+          const u64 sg = pack2(rcp_approx(1.0f + ex2_approx(e0)), rcp_approx(1.0f + ex2_approx(e1)));
+          y = mul2(y, mul2(FZ[p], sg));
+        }
+        unpack2(y, out[2 * p], out[2 * p + 1]);
+      }
+      if (fvalid) {
+        if (RP == 2) *reinterpret_cast<float4*>(fy) = make_float4(out[0], out[1], out[R - 2], out[R - 1]);
+        else *reinterpret_cast<float2*>(fy) = make_float2(out[0], out[1]);
+      }
+    };
+
+    // One barrier per chunk, at the start of its LAST block of four steps: by then every thread's part of chunk
+    // c + 1 has landed (wait_group), after it that chunk is visible to all, and every thread has left chunk c - 1,
+    // whose stage takes the request for chunk c + 2.  Placed there — not at the top of a chunk — the set-up
+    // of step 0 of the next chunk runs behind the last step of this one like any other step's, instead of as a
+    // serial MUFU chain at every chunk start.
+    cp_async_wait<NST - 2>();
+    __syncthreads();                        // the piece's first chunk is in place
+    Pre pre;
+    {
+      u64 DT[RP], X[RP];
+      Raw w;
+      load_dx(DT, X, sDt(0) + rl0, sX(0) + rl0, 0);
+      mufu_phase(DT, X, w);
+      pack_phase(w, s_carry, pre);
+    }
+    for (int c = cb; c < ce; ++c) {
+      const int st = (c - cb) % NST, stn = (c + 1 - cb) % NST;
+      const int64_t tc0 = (int64_t)c * TCH;
+      const int tcn = (int)((L - tc0) < TCH ? (L - tc0) : TCH);
+      if (last_piece && c + 1 == ce) pdl_trigger();   // single-wave long runner: let the next kernel queue up late
+      const float* pB = sB(st) + 4 * j;
+      const float* pC = sC(st) + 4 * j;
+      const float* pX = sX(st) + rl0;
+      const float* pD = sDt(st) + rl0;
+      const float* pZ = sZ(st) + rl0;
+      // one block of four steps is the loop body (not the whole chunk as in scan_seq_kernel): 200 instructions per
+      // step for RP = 2, and a 16-step body (48 KB of code) ran out of instruction cache ("no instruction" was the
+      // top stall reason in the first capture of this kernel)
+#pragma unroll 1
+      for (int g4 = 0; g4 < TCH; g4 += 4) {
+        if (g4 >= tcn) break;
+        const bool last_block = g4 + 4 == TCH;
+        if (last_block) {
+          cp_async_wait<0>();                 // chunk c + 1 (the only request in flight) has landed
+          __syncthreads();
+          issue();                            // chunk c + 2, into the stage chunk c - 1 has just left
+        }
+        // dt / x of the step after this block's last: row 0 of the next chunk's stage at the end of a chunk
+        const float* pDl = last_block ? sDt(stn) + rl0 : pD + (g4 + 4) * LDR;
+        const float* pXl = last_block ? sX(stn) + rl0 : pX + (g4 + 4) * LDR;
+        u64 yp[NV];      // index RP * i + p : step i of the block, row pair p
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = g4 + i;
+          u64 DTn[RP], Xn[RP];
+          Raw w;
+          Pre npre;
+          if (i < 3) load_dx(DTn, Xn, pD, pX, t + 1);
+          else load_dx(DTn, Xn, pDl, pXl, 0);
+          u64 P[RP][4], acc[RP][2];
+#pragma unroll
+          for (int p = 0; p < RP; ++p) {
+            P[p][0] = pre.ER[p];
+            P[p][1] = mul2(pre.ER[p], pre.R1[p]);
+            P[p][2] = mul2(pre.ER[p], pre.R2[p]);
+            P[p][3] = mul2(P[p][1], pre.R2[p]);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const float4 bq = *reinterpret_cast<const float4*>(pB + t * N + 16 * m);
+            const float4 cq = *reinterpret_cast<const float4*>(pC + t * N + 16 * m);
+            const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+            const float cv[4] = {cq.x, cq.y, cq.z, cq.w};
+#pragma unroll
+            for (int p = 0; p < RP; ++p) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                u64& h = H[p][4 * m + q];
+                h = fma2(P[p][q], h, bcast2(bv[q]));
+                if (m == 0 && q < 2) acc[p][q] = mul2(h, bcast2(cv[q]));
+                else acc[p][q & 1] = fma2(h, bcast2(cv[q]), acc[p][q & 1]);
+                if (m < 3) P[p][q] = mul2(P[p][q], pre.RQ[p]);
+              }
+            }
+            if (m == 0) mufu_phase(DTn, Xn, w);       // the MUFU results of step t+1 mature behind the FMA work
+          }
+#pragma unroll
+          for (int p = 0; p < RP; ++p) {
+            yp[RP * i + p] = mul2(add2(acc[p][0], acc[p][1]), pre.S[p]);
+            s_carry[p] = pre.S[p];
+          }
+          pack_phase(w, s_carry, npre);
+          pre = npre;
+        }
+        // x and z of the step this lane will finalise one block from now
+        u64 nFX[RP], nFZ[RP];
+        const int s0 = g4 + j;
+        if (RP == 2) {
+          const ulonglong2 x2 = *reinterpret_cast<const ulonglong2*>(pX + s0 * LDR);
+          nFX[0] = x2.x; nFX[RP - 1] = x2.y;
+          if (gate) {
+            const ulonglong2 z2 = *reinterpret_cast<const ulonglong2*>(pZ + s0 * LDR);
+            nFZ[0] = z2.x; nFZ[RP - 1] = z2.y;
+          } else {
+            nFZ[0] = nFZ[RP - 1] = 0ull;
+          }
+        } else {
+          nFX[0] = *reinterpret_cast<const u64*>(pX + s0 * LDR);
+          nFZ[0] = gate ? *reinterpret_cast<const u64*>(pZ + s0 * LDR) : 0ull;
+        }
+        finalize();                          // the PREVIOUS block
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ypv[i] = yp[i];
+#pragma unroll
+        for (int p = 0; p < RP; ++p) { FX[p] = nFX[p]; FZ[p] = nFZ[p]; }
+        fy = gY + (tc0 + s0) * a.ldy;
+        fvalid = s0 < tcn;
+      }
+    }
+    finalize();
+    cp_async_wait<0>();
+
+    if (save_state) {       // hand the chain over to the next slot
+      u64* st = sa.state + (size_t)blockIdx.x * THREADS * SW + tid;
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) __stcg(st + (size_t)(p * 16 + k) * THREADS, H[p][k]);
+        __stcg(st + (size_t)(RP * 16 + p) * THREADS, s_carry[p]);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) *reinterpret_cast<volatile unsigned int*>(sa.flags + blockIdx.x) = sa.epoch;
+    } else {
+      __syncthreads();      // the next piece re-uses the tile stages
+    }
+  }
+}
+
+// Row-packed kernel, two shapes with identical per-row arithmetic (a row's result does not depend on which one ran,
+// nor on where the time axis was cut): 128-row CTAs (two row pairs per lane) when that still gives every SM a
+// chain, 64-row CTAs (one pair per lane) for smaller batches.
+constexpr int RP_WARPS = 4;
+template <int RP, int OCC = 3>
+struct RpCfg {
+  static constexpr int ROWS = RP_WARPS * 8 * 2 * RP;
+  static constexpr int THREADS = RP_WARPS * 32;
+  static constexpr size_t SMEM = (size_t)3 * TCH * (2 * 64 + 3 * (ROWS + 8)) * sizeof(float);
+  static constexpr size_t STATE_BYTES = (size_t)THREADS * RP * 17 * sizeof(unsigned long long);   // per slot
+};
+constexpr int RP_MAX_SLOTS = 1024;
+constexpr size_t RP_SCRATCH_BYTES = 4096 + (size_t)RP_MAX_SLOTS * RpCfg<2>::STATE_BYTES;
+
+// Hand-over scratch of the time split: one per (device, stream), made on first use and kept.  Launches on one
+// stream are serialised, so they can share it; the flags are zeroed once and every launch uses a new epoch.
+// (A captured CUDA graph would replay a stale epoch: launch_selective_scan is not graph-capturable when it splits.)
+struct RpScratch {
+  void* mem = nullptr;
+  unsigned int epoch = 0;
+};
+cudaError_t rp_scratch(cudaStream_t s, RpScratch** out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, RpScratch> cache;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  RpScratch& sc = cache[std::make_pair(dev, s)];
+  if (!sc.mem) {
+    e = cudaMalloc(&sc.mem, RP_SCRATCH_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(sc.mem, 0, 4096);
+    if (e != cudaSuccess) return e;
+  }
+  *out = &sc;
+  return cudaSuccess;
+}
+
+// true when the row-packed kernel takes this problem: true recurrence, structured A, N = 64, whole CTAs of rows,
+// 16-byte aligned rows
+bool rp_takes(const ScanArgs& a) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.parallel_quirk || !a.structured_a || a.N != 64 || a.Di % RpCfg<1>::ROWS != 0) return false;
+  if ((a.ldx & 3) || (a.lddt & 3) || (a.ldy & 3) || (a.ldb & 3) || (a.ldc & 3)) return false;
+  if (!al16(a.x) || !al16(a.dt) || !al16(a.y) || !al16(a.Bm) || !al16(a.Cm)) return false;
+  if (a.z && ((a.ldz & 3) || !al16(a.z))) return false;
+  return true;
+}
+
+template <int RP, int OCC>
+cudaError_t launch_rp_cfg(const ScanArgs& a, int sms, cudaStream_t s) {
+  using C = RpCfg<RP, OCC>;
+  auto kernel = scan_rp_kernel<RP, RP_WARPS, OCC>;
+  static int occ = -1;
+  cudaError_t e = cudaSuccess;
+  if (occ < 0) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, C::THREADS, C::SMEM);
+    if (e != cudaSuccess) return e;
+    occ = n;
+  }
+  const int64_t n_chains = a.B * (a.Di / C::ROWS);
+  const int64_t total = n_chains * ((a.L + TCH - 1) / TCH);
+  SplitArgs sa;
+  unsigned grid = (unsigned)n_chains;
+  // Time split into two slots per SM, when there are more chains than that and they do not divide evenly.  What a
+  // split can and cannot do (tools/scan_variants.sh, batch 64 x 751): a chain stays 751 sequential steps whose pace
+  // is set by how many warps share its sub-partition, so cutting chains that already fit the resident slots only
+  // adds co-residents and slows every chain (444 slots: 0.264 ms; 296: 0.252; unsplit 384 CTAs: 0.269); the gain
+  // is in evening out MORE chains than slots (1.3 chains per slot instead of 3 CTAs on some SMs and 2 on others).
+  // A slot may wait for its predecessor only, which the hardware dispatched before it (CTAs are dealt out in index
+  // order).
+  int64_t slots = (int64_t)(occ < 2 ? occ : 2) * sms;
+  if (slots > RP_MAX_SLOTS) slots = RP_MAX_SLOTS;
+  if (slots > total) slots = total;
+  static const int split_env = debug_env_int("VASR_SCAN_SPLIT", -1);     // -1: rule below; 0: never; n > 0: n slots
+  if (split_env > 0 && split_env <= (int64_t)occ * sms && split_env <= RP_MAX_SLOTS) slots = split_env;
+  bool split = occ > 0 && n_chains > slots && slots >= 1 && n_chains % slots != 0;
+  if (split_env == 0) split = false;
+  if (split) {
+    RpScratch* sc = nullptr;
+    e = rp_scratch(s, &sc);
+    if (e != cudaSuccess) return e;
+    sa.n_slots = (int)slots;
+    sa.flags = reinterpret_cast<unsigned int*>(sc->mem);
+    sa.state = reinterpret_cast<u64*>(reinterpret_cast<char*>(sc->mem) + 4096);
+    sa.epoch = ++sc->epoch;
+    grid = (unsigned)slots;
+  }
+  return launch_k(kernel, dim3(grid), dim3(C::THREADS), C::SMEM, s, a, sa);
+}
+
+cudaError_t launch_rp(const ScanArgs& a, cudaStream_t s) {
+  const int sms = a.num_sms > 0 ? a.num_sms : 148;
+  static const int rp_env = debug_env_int("VASR_SCAN_RP", 0);            // 1 / 2: force the CTA shape
+  // 128-row CTAs once they fill two slots per SM (batch 128: 0.42 ms against 0.47 for 64-row CTAs and 0.50 for
+  // scan_seq_kernel); below that the 64-row shape keeps more chains in flight (batch 64: 0.252 against 0.308)
+  const bool wide = rp_env ? rp_env == 2 : a.B * (a.Di / RpCfg<2>::ROWS) >= 2 * sms;
+  if (a.Di % RpCfg<2>::ROWS == 0 && wide) {
+    return launch_rp_cfg<2, 2>(a, sms, s);
+  }
+  return launch_rp_cfg<1, 3>(a, sms, s);
+}
+
 template <int LPR, int WARPS, int RPL>
 cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
   constexpr int N = LPR * 16;
@@ -714,6 +1252,12 @@ cudaError_t launch_selective_scan(const ScanArgs& a, cudaStream_t s, int64_t* la
       (reinterpret_cast<uintptr_t>(a.Cm) & 15))
     return cudaErrorInvalidValue;
   cudaError_t e;
+  static const int old_env = debug_env_int("VASR_SCAN_OLD", 0);          // 1: scan_seq_kernel for every shape
+  if (rp_takes(a) && !old_env) {
+    e = launch_rp(a, s);
+    if (launches && e == cudaSuccess) ++*launches;
+    return e;
+  }
   switch (a.N) {
     case 64: e = launch_lpr<8>(a, s); break;
     case 32: e = launch_lpr<4>(a, s); break;
