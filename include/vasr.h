@@ -171,6 +171,14 @@ int vasr_set_quantization(vasr_handle* h, int enabled);
 int vasr_calibrate(vasr_handle* h, const float* mel_dev, int64_t B, int64_t T, void* stream);
 int vasr_get_quant_params(vasr_handle* h, const char* module, float* scale, float* zero_point);
 int vasr_set_quant_params(vasr_handle* h, const char* module, float scale, float zero_point);
+/* One quantised projection on its own (parity seam for QuantizedLinear.forward / QuantizedConv1d.forward,
+ * quantize.py:180-191, 248-266): the projection that hosts `module` — fused neighbours included: k_proj | v_proj
+ * share one, gate_proj.0 | local_proj | global_proj another (input [local | ctx]) — on x (B, R, K) with its
+ * fake-quantised weights, bias and output FakeQuantize, no activation.  For temporal_binding.conv x is the mel
+ * (B, R = T, mel_bins) and out has (R + 1) / 2 rows per utterance.  out: (B, R_out, N) with N the projection's
+ * full width; *n_out, *col0, *ncol (may be NULL) receive N and the column range of `module` inside it. */
+int vasr_quant_site(vasr_handle* h, const char* module, const float* x_dev, int64_t B, int64_t R, float* out_dev,
+                    int32_t* n_out, int32_t* col0, int32_t* ncol, void* stream);
 
 /* ---- a plain linear layer (F.linear), exposed so the GEMM kernel can be tested alone.
  * act: 0 none, 1 gelu(erf), 2 softplus, 3 sigmoid.  x (M, K) stride ldx, w (N, K), bias (N) or

@@ -54,8 +54,24 @@ logits_cal = qmodel(mel_cal).numpy()
 for m in fqs:
     m.calibrated.fill_(True)
     m.eval()
-logits_q = qmodel(mel_test).numpy()
 mods = dict(qmodel.named_modules())
+# input and output of each of the 12 quantised modules during the frozen forward: the per-module parity fixture
+captured = {}
+hooks = [mods[n].register_forward_hook(
+    lambda m, inp, out, n=n: captured.__setitem__(n, (inp[0].detach().clone(), out.detach().clone()))) for n in names]
+logits_q = qmodel(mel_test).numpy()
+for hk in hooks:
+    hk.remove()
+per_module = {}
+for n in names:
+    xin, yout = captured[n]
+    if n == "temporal_binding.conv":            # Conv1d sees (B, C, T) and returns (B, C, L): store (B, T, C) / (B, L, C)
+        xin, yout = xin.transpose(1, 2), yout.transpose(1, 2)
+    per_module[n + ":in"] = xin.contiguous().numpy()
+    per_module[n + ":out"] = yout.contiguous().numpy()
+mpath = os.path.join(HERE, "quant_modules.npz")
+np.savez_compressed(mpath, names=np.array(names), **per_module)
+print("quant_modules.npz", os.path.getsize(mpath) // 1024, "KiB")
 act_scale = np.array([float(mods[n].activation_quantizer.scale) for n in names], dtype=np.float64)
 act_zp = np.array([float(mods[n].activation_quantizer.zero_point) for n in names], dtype=np.float64)
 # quantised weight of one module, as the forward pass sees it

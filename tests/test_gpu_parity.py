@@ -269,6 +269,38 @@ def test_scan_large_batch_time_split(va, B, L):
     assert (np.abs(alone.cpu().numpy() - got[:1]) / scale[:1]).max() < 2e-5
 
 
+@pytest.mark.parametrize("n,structured", [(64, True), (32, True), (64, False)])
+def test_scan_parallel_mode_dead_state_shortcuts(va, n, structured):
+    """The reference's 'parallel' rule multiplies every new term by exp(A cumsum(dt)); once that is an exact fp32
+    zero for all rows of a CTA the kernel copies hP from the parent index (phase 2) and from the next power of two
+    on emits x D only (phase 3).  Against the oracle on a sequence long enough for all three phases, with rows that
+    die at different times, and bit for bit against the same rows computed next to a row that never dies (that CTA
+    runs the full rule throughout)."""
+    B, L, Di = 2, 700, 128
+    x, dt, A, Bm, Cm, D = FU.scan_inputs(B, L, Di, n, seed=900 + n, structured_a=structured)
+    dt[:, :, 32:48] *= 0.4                                     # a CTA whose rows die later than the others
+    dt[1, :, 64:80] *= 0.02                                    # a CTA (batch 1, rows 64..79) that never dies
+    rs = np.random.RandomState(n)
+    z = rs.standard_normal(x.shape).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    got = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="parallel")
+    d = lambda a: a.astype(np.float64)
+    ref = O.selective_scan(d(x), d(dt), d(A), d(Bm), d(Cm), d(D), "parallel") * O.silu(d(z))
+    assert rel(got, ref) < 1e-4
+    tail = got[:, 512:].cpu().numpy()                         # far beyond the decay horizon of the ordinary rows
+    plain = (x * D)[:, 512:] * (z / (1 + np.exp(-z.astype(np.float64))))[:, 512:]
+    assert np.abs(tail[0] - plain[0]).max() < 1e-5            # phase 3: y = x D silu(z)
+    # one never-dying row per CTA of 8 or 16 rows keeps every CTA in the full rule; the other rows must not notice
+    dt2 = dt.copy()
+    dt2[:, :, ::8] *= 0.01
+    keep = np.ones(Di, dtype=bool); keep[::8] = False
+    a1 = va.selective_scan(t(x), t(dt), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="parallel")[:, :, torch.from_numpy(keep).cuda()]
+    a2 = va.selective_scan(t(x), t(dt2), t(A), t(Bm), t(Cm), t(D), z=t(z), scan_mode="parallel")[:, :, torch.from_numpy(keep).cuda()]
+    assert torch.equal(a1, a2)
+    with pytest.raises(ValueError):
+        va.selective_scan(t(x), t(-dt), t(A), t(Bm), t(Cm), t(D), scan_mode="parallel")
+
+
 def test_scan_mamba_signature(va):
     x, dt, A, Bm, Cm, D = FU.scan_inputs(2, 50, 384, 64, 77, True)
     t = lambda a: torch.from_numpy(a).cuda()
@@ -609,6 +641,40 @@ def test_quantized_model_matches_reference_golden(va, golden):
     # tokens: fused path == separate calls, and agree with the reference's argmax stream
     audio = FU.synth_audio(2, 16000, seed=77)
     assert m.transcribe(audio.cuda()) == va.ctc_greedy_decode(m(mel_test))
+
+
+def test_quantized_modules_one_by_one(va, golden):
+    """Each of the 12 quantised modules on its own, fed the INPUT the reference's module saw in its frozen
+    forward (tests/golden/quant_modules.npz, forward hooks in make_golden_quant.py) with the reference's
+    calibrated scale / zero point: the output must sit on the same grid point everywhere, one quantiser step
+    at most where the fp32 value lands within rounding noise of a grid boundary.  This separates "a quantiser
+    upstream flipped a step" (what the whole-model test tolerates) from a wrong module."""
+    from velocity_asr.quantize import run_quantized_module
+    g, gm = golden("quant"), golden("quant_modules")
+    names = [str(n) for n in g["names"]]
+    m = make_model(va, "sequential")
+    va.prepare_model_for_qat(m)
+    eng = m._engine(m._device())
+    for n, s_ref, z_ref in zip(names, g["act_scale"], g["act_zp"]):
+        va._native.check(eng.lib.vasr_set_quant_params(eng.handle, n.encode(), float(s_ref), float(z_ref)))
+    m._act_qparams = {n: (float(s_), float(z_)) for n, s_, z_ in zip(names, g["act_scale"], g["act_zp"])}
+    site_input = {n: gm[n + ":in"] for n in names}
+    # gate_proj.0 / local_proj / global_proj share the projection whose input is [local | ctx]
+    cat = np.concatenate([gm["global_context.fusion.local_proj:in"], gm["global_context.fusion.global_proj:in"]], -1)
+    assert np.array_equal(cat, gm["global_context.fusion.gate_proj.0:in"])
+    for n in ("global_context.fusion.local_proj", "global_context.fusion.global_proj"):
+        site_input[n] = cat
+    exact_total = 0
+    for n, step in zip(names, g["act_scale"]):
+        want = gm[n + ":out"]
+        got = run_quantized_module(m, n, torch.from_numpy(site_input[n]).cuda()).cpu().numpy()
+        assert got.shape == want.shape, n
+        d = np.abs(got - want)
+        assert d.max() <= 1.001 * step + 1e-6, (n, d.max(), step)
+        exact = (d < 1e-3 * step).mean()
+        assert exact > 0.995, (n, exact)                     # off-grid-by-one only at boundary ties
+        exact_total += exact
+    assert exact_total / len(names) > 0.999
 
 
 def test_quantization_is_reversible_and_guarded(va):

@@ -218,3 +218,24 @@ def test_config2_utterance_at_benchmark_size(golden, mode):
     if safe.all():
         want = [t for t in g[mode + "_tokens"][row].tolist() if t >= 0]
         assert O.ctc_greedy_decode(logits)[0] == want
+
+
+def test_quantized_modules_one_by_one(golden):
+    """The oracle's QuantizedLinear / QuantizedConv1d arithmetic (quantize.py:180-191, 248-266) on the recorded input
+    of each of the 12 modules of the reference's frozen forward: same grid point, one step at most at boundary ties."""
+    g, gm = golden("quant"), golden("quant_modules")
+    sd = {k: v.numpy() for k, v in seeded_state_dict().items()}
+    for n, scale, zp in zip([str(x) for x in g["names"]], g["act_scale"], g["act_zp"]):
+        x, want = gm[n + ":in"].astype(np.float32), gm[n + ":out"]
+        w = O.quantized_weight(sd[n + ".weight"].astype(np.float32))
+        if n == "temporal_binding.conv":                       # stride 2, kernel 3, padding 1 as a projection of 3 frames
+            xp = np.pad(x, ((0, 0), (1, 1), (0, 0)))
+            L = want.shape[1]
+            frames = np.stack([xp[:, 2 * l:2 * l + 3] for l in range(L)], 1)            # (B, L, 3, mel)
+            out = np.einsum("blkc,ock->blo", frames, w) + sd[n + ".bias"]
+        else:
+            out = x @ w.T + sd[n + ".bias"]
+        out = O.fake_quantize(out.astype(np.float32), np.float32(scale), np.float32(zp), symmetric=False)
+        d = np.abs(out - want)
+        assert d.max() <= 1.001 * scale + 1e-6, (n, d.max(), scale)
+        assert (d < 1e-3 * scale).mean() > 0.995, n

@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_ref.js
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_ncu.log 2>&1
 python tools/scan_bench.py --quick > gpurun_out/${tag}_scan_bench.json 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:scan_seq -c 1 -f -o gpurun_out/${tag}_scan_full \
+ncu --set full --clock-control none --import-source on -k "regex:scan_rp|scan_seq" -c 1 -f -o gpurun_out/${tag}_scan_full \
     python tools/scan_bench.py --quick > gpurun_out/${tag}_scan_ncu.log 2>&1 && \
 python tools/ncu_scan_json.py gpurun_out/${tag}_scan_full.ncu-rep 64 751 384 64 > gpurun_out/${tag}_scan_ncu.json
 tail -3 gpurun_out/${tag}_pytest.log

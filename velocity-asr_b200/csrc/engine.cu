@@ -1301,6 +1301,46 @@ int vasr_set_quant_params(vasr_handle* h, const char* module, float scale, float
   return VASR_OK;
 }
 
+int vasr_quant_site(vasr_handle* h, const char* module, const float* x_dev, int64_t B, int64_t R, float* out_dev,
+                    int32_t* n_out, int32_t* col0, int32_t* ncol, void* stream) {
+  RET(check_ready(h));
+  if (!module) return fail(VASR_ERR_INVALID, "null argument");
+  if (!h->quant_active) return fail(VASR_ERR_STATE, "quantisation is not enabled (vasr_set_quantization + commit)");
+  int j = 0;
+  QSite* q = find_module(h, module, &j);
+  if (!q) return fail(VASR_ERR_INVALID, std::string("not a quantised module: ") + module);
+  const int site = (int)(q - h->qsite);
+  if (n_out) *n_out = q->N;
+  if (col0) *col0 = q->c0[j];
+  if (ncol) *ncol = q->nc[j];
+  if (!x_dev || !out_dev) return B * R > 0 ? fail(VASR_ERR_INVALID, "null argument") : VASR_OK;
+  if (B <= 0 || R <= 0) return VASR_OK;
+  DeviceGuard dev_guard(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CallOrder call_order(h, s);
+  const int d = h->cfg.d_model, att = h->cfg.attention_dim;
+  GemmArgs g;
+  g.act = ACT_NONE;
+  g.C = out_dev; g.ldc = q->N; g.N = q->N;
+  if (site == Q_TB) {
+    const Dims dm = make_dims(h, B, 0, R);
+    Work k;
+    RET(ensure_workspace(h, dm, false, false, &k));
+    KL(launch_mel_finish(x_dev, nullptr, nullptr, k.melpad, dm.B, dm.T, dm.n_mels, dm.Tp, 1, s, &h->launches));
+    g.A = k.melpad; g.lda = 2 * dm.n_mels; g.rows_per_batch = dm.L; g.batch_stride = dm.Tp * dm.n_mels;
+    g.W = h->tb_w; g.bias = h->tb_b; g.M = dm.M; g.K = 3 * dm.n_mels;
+  } else {
+    struct { const float* w; const float* b; int K; } tab[Q_SITES] = {
+        {nullptr, nullptr, 0}, {h->p1_w, h->p1_b, d}, {h->p2_w, h->p2_b, d}, {h->w_q, h->b_q, d},
+        {h->w_kv, h->b_kv, d}, {h->w_o, h->b_o, att}, {h->w_f3, h->b_f3, 2 * d}, {h->w_fo, h->b_fo, d},
+        {h->w_ctc, h->b_ctc, d}};
+    g.A = x_dev; g.lda = tab[site].K; g.W = tab[site].w; g.bias = tab[site].b; g.M = B * R; g.K = tab[site].K;
+  }
+  g.q_scale = q->qs;
+  g.q_zp = q->qz;
+  return gemm(h, g, s);
+}
+
 int vasr_split_tf32(const float* w_dev, float* split_dev, int64_t numel, void* stream) {
   if (!w_dev || !split_dev || numel < 0) return fail(VASR_ERR_INVALID, "null argument");
   KL(launch_split_tf32(w_dev, split_dev, numel, static_cast<cudaStream_t>(stream)));

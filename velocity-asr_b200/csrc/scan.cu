@@ -69,8 +69,23 @@ __device__ __forceinline__ void powers_generic(float s, const float (&al2)[SPL],
 // compile time for seven of the eight steps:  parent(8q+i) = 8q + (i & (i-1)).  Ancestor levels
 // 1..3 ("most recent index with at least l trailing zeros") therefore live in registers; only the
 // step at 8q touches the higher levels, which sit in local memory (one read, ~one write per 8 steps).
+//
+// Where the quirk stops costing anything.  Every term that enters hP[t] carries the factor exp(A S[t]), the decay
+// from time 0, and S only grows (dt is a softplus output, ssm.py:118).  Once min_n |A[n]| S[t] log2(e) >= 160 that
+// factor is exactly 0 in fp32 for every state (this kernel's ex2.approx.ftz and the reference's product of dA
+// alike), so hP[t] = hP[parent(t)] bit for bit from then on, and the true state H is never needed again:
+//   phase 1  (until every row of the CTA has passed that point, checked once per 16-step chunk): the full rule;
+//   phase 2  (from there to the next power of two P2): hP[t] = hP[parent(t)], y = <hP[t], C[t]> + x D — one FMA
+//            per state, no B, no dt;
+//   phase 3  (t >= P2): every ancestor of t is >= P2 or 0, so hP[t] = hP[0] = 0 and y = x D (gated): a plain
+//            streaming pass over x and z.
+// Phases 2 and 3 are shortcuts of phase 1, not approximations: the full rule computes the same bits (it multiplies
+// by an exact zero), so a row's result does not depend on its CTA mates or on where the switch falls.  With the
+// reference's random-init weights dt ~ 0.7 and the switch comes after ~150 of config 2's 751 tokens; a model whose
+// dt stays small (sum of dt below ~110 over the utterance) runs phase 1 throughout.
 // ------------------------------------------------------------------------------------------
 constexpr int TCQ = 16;
+constexpr float QUIRK_DEAD_LOG2 = 160.0f;     // exp(A S) < 2^-160: zero in fp32, denormals included
 
 struct Anc {
   State8 hp, H;
@@ -106,6 +121,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   for (int k = 0; k < SPL; ++k) al2[k] = a.A[n0 + k] * LOG2E;
   const float n0p1 = (float)(n0 + 1);
   const float Dd = a.D ? a.D[d0 + rl] : 0.f;
+  float amin_l2 = 3.0e38f;                    // min_n |A[n]| log2 e: the slowest-decaying state
+#pragma unroll
+  for (int k = 0; k < SPL; ++k) amin_l2 = fminf(amin_l2, fabsf(al2[k]));
+#pragma unroll
+  for (int o = 1; o < LPR; o <<= 1) amin_l2 = fminf(amin_l2, __shfl_xor_sync(0xffffffffu, amin_l2, o));
+  bool frozen = false;                        // phase 2: hP[t] = hP[parent(t)]
+  int64_t t_zero = L;                         // phase 3 starts here (a power of two >= the start of phase 2)
 
   Anc cur, a1, a2, a3;
 #pragma unroll
@@ -125,7 +147,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
     for (int k = 0; k < SPL; ++k) hi_hp[l][k] = hi_H[l][k] = 0.f;
   }
 
-  for (int64_t tc0 = 0; tc0 < L; tc0 += TCQ) {
+  int64_t tc0 = 0;
+  for (; tc0 < L && tc0 < t_zero; tc0 += TCQ) {
     if (tc0 + TCQ >= L) pdl_trigger();     // last chunk: see scan_seq_kernel
     const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
     for (int idx = tid; idx < TCQ * (N / 4); idx += SCAN_THREADS) {
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
       float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vc = vb;
       if (t < tcn) {
         const int64_t row = b * L + tc0 + t;
-        vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
+        if (!frozen) vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
         vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
       }
       const int slot = (f & 1) * LPR + (f >> 1);   // conflict-free 16-byte phases (see below)
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
       if (t < tcn) {
         const int64_t row = b * L + tc0 + t;
         vx = __ldg(a.x + row * a.ldx + d0 + r);
-        vd = __ldg(a.dt + row * a.lddt + d0 + r);
+        if (!frozen) vd = __ldg(a.dt + row * a.lddt + d0 + r);
         if (gate) vz = __ldg(a.z + row * a.ldz + d0 + r);
       }
       sx[t][r] = vx;
@@ -166,7 +189,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
         const float xv = sx[t][rl];
         const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * j]);
         const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * (LPR + j)]);
-        if (has_parent) {
+        if (has_parent && frozen) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cur.hp.v[k] = par.hp.v[k];
+        } else if (has_parent) {
           const float Sf = (float)cur.S;
           const float dS = (float)(cur.S - par.S);
           State8 q, pd;
@@ -192,6 +218,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
         yp[i] = hsum2(add2(acc, acc2));
       };
       auto advance = [&](int i) {
+        if (frozen) return;                   // H and S feed nothing any more
         const int t = g8 + i;
         const float dtv = sdt[t][rl];
         State8 p;
@@ -267,10 +294,64 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
         sy[t][rl] = yv;
       }
     }
-    __syncthreads();
+    // phase switch, once per chunk: has every row of the CTA decayed to an exact zero?
+    const bool dead = frozen || (float)cur.S * amin_l2 >= QUIRK_DEAD_LOG2;
+    const bool all_dead = __syncthreads_and(dead) != 0;       // also orders sy before the stores below
+    if (all_dead && !frozen) {
+      frozen = true;
+      int64_t p2 = TCQ;
+      while (p2 < tc0 + TCQ) p2 <<= 1;
+      t_zero = p2;
+    }
     for (int idx = tid; idx < tcn * ROWS; idx += SCAN_THREADS) {
       const int t = idx / ROWS, r = idx % ROWS;
       a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
+    }
+  }
+  // phase 3: hP = 0 for every remaining t, y = x D (gated)
+  if (tc0 < L) {
+    pdl_trigger();
+    auto one = [&](float xv, float dv, float zv) {            // the same operations as the chunk loop with yp = 0
+      float yv = 0.f + xv * dv;
+      if (gate) yv *= zv / (1.0f + __expf(-zv));
+      return yv;
+    };
+    const bool vec = !((a.ldx | a.ldy | (gate ? a.ldz : 0)) & 3) && !((reinterpret_cast<uintptr_t>(a.x) |
+                     reinterpret_cast<uintptr_t>(a.y) | (gate ? reinterpret_cast<uintptr_t>(a.z) : 0)) & 15);
+    if (vec) {                   // float4 pieces of a timestep's ROWS values, four independent pieces in flight
+      constexpr int RQ = ROWS / 4;
+      const int q4 = (tid % RQ) * 4;
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.D) dv = make_float4(a.D[d0 + q4], a.D[d0 + q4 + 1], a.D[d0 + q4 + 2], a.D[d0 + q4 + 3]);
+      const int64_t n_t = L - tc0;
+      constexpr int TS = SCAN_THREADS / RQ;                    // timesteps covered per pass of the CTA
+      for (int64_t t0 = tid / RQ; t0 < n_t; t0 += 4 * TS) {
+        float4 xv[4], zv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t t = t0 + u * TS;
+          const int64_t row = b * L + tc0 + (t < n_t ? t : t0);
+          xv[u] = __ldg(reinterpret_cast<const float4*>(a.x + row * a.ldx + d0 + q4));
+          zv[u] = gate ? __ldg(reinterpret_cast<const float4*>(a.z + row * a.ldz + d0 + q4)) : dv;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t t = t0 + u * TS;
+          if (t < n_t) {
+            const int64_t row = b * L + tc0 + t;
+            *reinterpret_cast<float4*>(a.y + row * a.ldy + d0 + q4) =
+                make_float4(one(xv[u].x, dv.x, zv[u].x), one(xv[u].y, dv.y, zv[u].y), one(xv[u].z, dv.z, zv[u].z),
+                            one(xv[u].w, dv.w, zv[u].w));
+          }
+        }
+      }
+    } else {
+      for (int64_t idx = tid; idx < (L - tc0) * ROWS; idx += SCAN_THREADS) {
+        const int64_t row = b * L + tc0 + idx / ROWS;
+        const int r = (int)(idx % ROWS);
+        a.y[row * a.ldy + d0 + r] = one(__ldg(a.x + row * a.ldx + d0 + r), a.D ? __ldg(a.D + d0 + r) : 0.f,
+                                        gate ? __ldg(a.z + row * a.ldz + d0 + r) : 0.f);
+      }
     }
   }
 }
@@ -1133,10 +1214,15 @@ template <int RP, int OCC>
 cudaError_t launch_rp_cfg(const ScanArgs& a, int sms, cudaStream_t s) {
   using C = RpCfg<RP, OCC>;
   auto kernel = scan_rp_kernel<RP, RP_WARPS, OCC>;
+  // A split launch asks for at least SPLIT_SMEM bytes of shared memory, more than a third of an SM's: never more
+  // than two CTAs per SM.  The slots are dealt two per SM; under programmatic launch the CTAs arrive while the
+  // previous kernel drains, and with room for three the SMs that free first took three slots and left others with
+  // one (step 5.47 -> 6.02 ms before this cap).
+  constexpr size_t SPLIT_SMEM = C::SMEM > 78 * 1024 ? C::SMEM : 78 * 1024;
   static int occ = -1;
   cudaError_t e = cudaSuccess;
   if (occ < 0) {
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPLIT_SMEM);
     if (e != cudaSuccess) return e;
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, C::THREADS, C::SMEM);
@@ -1147,6 +1233,7 @@ cudaError_t launch_rp_cfg(const ScanArgs& a, int sms, cudaStream_t s) {
   const int64_t total = n_chains * ((a.L + TCH - 1) / TCH);
   SplitArgs sa;
   unsigned grid = (unsigned)n_chains;
+  size_t smem = C::SMEM;
   // Time split into two slots per SM, when there are more chains than that and they do not divide evenly.  What a
   // split can and cannot do (tools/scan_variants.sh, batch 64 x 751): a chain stays 751 sequential steps whose pace
   // is set by how many warps share its sub-partition, so cutting chains that already fit the resident slots only
@@ -1170,8 +1257,9 @@ cudaError_t launch_rp_cfg(const ScanArgs& a, int sms, cudaStream_t s) {
     sa.state = reinterpret_cast<u64*>(reinterpret_cast<char*>(sc->mem) + 4096);
     sa.epoch = ++sc->epoch;
     grid = (unsigned)slots;
+    smem = SPLIT_SMEM;
   }
-  return launch_k(kernel, dim3(grid), dim3(C::THREADS), C::SMEM, s, a, sa);
+  return launch_k(kernel, dim3(grid), dim3(C::THREADS), smem, s, a, sa);
 }
 
 cudaError_t launch_rp(const ScanArgs& a, cudaStream_t s) {

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "vasr_calibrate": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vasr_get_quant_params": (c_int, [c_void_p, c_char_p, POINTER(c_float), POINTER(c_float)]),
     "vasr_set_quant_params": (c_int, [c_void_p, c_char_p, c_float, c_float]),
+    "vasr_quant_site": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int32),
+                                POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "vasr_split_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vasr_linear_tc": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                c_int64, c_int64, c_int64, c_int, c_void_p]),

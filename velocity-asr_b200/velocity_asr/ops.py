@@ -18,17 +18,22 @@ def _f32c(t):
 
 def selective_scan(x: torch.Tensor, dt: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
                    D: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
-                   scan_mode: str = "sequential") -> torch.Tensor:
+                   scan_mode: str = "sequential", validate: bool = True) -> torch.Tensor:
     """x, dt: (B, L, Di); A: (N,); B, C: (B, L, N); D: (Di,) -> y (B, L, Di).
 
     scan_mode 'sequential' / 'mamba' = SelectiveSSM._sequential_scan (ssm.py:134-171);
     'parallel' = _parallel_scan exactly as shipped (ssm.py:173-295).  With z given, the result is
-    y * silu(z) (ssm.py:129).  N in {16, 32, 64}; Di a multiple of 64."""
+    y * silu(z) (ssm.py:129).  N in {16, 32, 64}; Di a multiple of 64.  validate=False skips the (synchronising)
+    check that dt is non-negative in 'parallel' mode."""
     if scan_mode not in _native.SCAN_MODE_ID:
         raise ValueError(f"Unknown scan_mode: {scan_mode}")
     if x.device.type != "cuda":
         raise RuntimeError("selective_scan runs on CUDA only (no CPU fallback)")
     x, dt, A, B, C, D, z = map(_f32c, (x, dt, A, B, C, D, z))
+    if validate and scan_mode == "parallel" and dt.numel() and bool((dt < 0).any()):
+        # the 'parallel' kernel stops evaluating terms once exp(A * cumsum(dt)) has decayed to an exact zero, which
+        # presumes a growing cumsum: dt is a softplus output wherever the reference calls its scan (ssm.py:118)
+        raise ValueError("selective_scan(scan_mode='parallel') needs dt >= 0 (dt is a softplus output, ssm.py:118)")
     Bsz, L, Di = x.shape
     N = A.numel()
     y = torch.empty_like(x)

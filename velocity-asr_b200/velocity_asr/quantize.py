@@ -93,3 +93,26 @@ def read_quant_params(model) -> Dict[str, Tuple[float, float]]:
         _native.check(eng.lib.vasr_get_quant_params(eng.handle, name.encode(), ctypes.byref(s), ctypes.byref(z)))
         out[name] = (s.value, z.value)
     return out
+
+
+def run_quantized_module(model, module: str, x: torch.Tensor) -> torch.Tensor:
+    """QuantizedLinear.forward / QuantizedConv1d.forward of one of the 12 replaced modules on its own
+    (quantize.py:180-191, 248-266): parity seam.  x is the input of the PROJECTION that hosts the module: the
+    module's own input, except that k_proj / v_proj share one projection and gate_proj.0 / local_proj / global_proj
+    another, whose input is [local | ctx] (B, L, 2 d_model); for temporal_binding.conv x is the mel (B, T, mel_bins).
+    Returns the module's output (B, rows, out_features)."""
+    if not getattr(model, "_quantized", False):
+        raise RuntimeError("call prepare_model_for_qat(model) first")
+    dev = model._exec_device(x)
+    eng = model._engine(dev)
+    x = x.to(dev, torch.float32).contiguous()
+    n, c0, nc = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    name = module.encode()
+    _native.check(eng.lib.vasr_quant_site(eng.handle, name, None, 0, 0, None, ctypes.byref(n), ctypes.byref(c0),
+                                          ctypes.byref(nc), None))
+    B, R = x.size(0), x.size(1)
+    rows = (R + 1) // 2 if module == "temporal_binding.conv" else R
+    out = torch.empty(B, rows, n.value, device=dev, dtype=torch.float32)
+    _native.check(eng.lib.vasr_quant_site(eng.handle, name, _native.ptr(x), B, R, _native.ptr(out), None, None, None,
+                                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out[:, :, c0.value:c0.value + nc.value]
