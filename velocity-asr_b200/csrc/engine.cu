@@ -118,6 +118,12 @@ struct vasr_handle {
 
   Arena ws;
   cudaStream_t own_stream = nullptr;
+  // host entry points: the PCM travels in HOST_SLICES pieces on copy_stream, the log-mel of a piece starts when it
+  // has landed (the mel is per utterance), so the front end runs under the tail of the transfer
+  static constexpr int HOST_SLICES = 8;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t slice_ev[HOST_SLICES] = {};
+  cudaEvent_t copy_gate = nullptr;
   int64_t launches = 0;
   // Calls on one handle share the workspace and the lazily built weight splits.  Each call leaves an event at
   // its end on its stream; a call arriving on ANOTHER stream (the *_host entry points use own_stream) waits for
@@ -660,6 +666,28 @@ int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int 
   return VASR_OK;
 }
 
+// Host PCM -> k.raw (+ partial statistics): HOST_SLICES transfers on copy_stream, each followed on `s` by the
+// log-mel of its utterances; then the statistics of the whole batch.
+int run_mel_from_host(vasr_handle* h, const Dims& q, const Work& k, const float* pcm_host, cudaStream_t s) {
+  const int64_t per = (q.B + vasr_handle::HOST_SLICES - 1) / vasr_handle::HOST_SLICES;
+  const int64_t nblk = mel_fft_blocks(q.T);
+  CK(cudaEventRecord(h->copy_gate, s));                        // the stage buffer is free once `s` got here
+  CK(cudaStreamWaitEvent(h->copy_stream, h->copy_gate, 0));
+  int i = 0;
+  for (int64_t b0 = 0; b0 < q.B; b0 += per, ++i) {
+    const int64_t nb = q.B - b0 < per ? q.B - b0 : per;
+    CK(cudaMemcpyAsync(k.pcm_stage + b0 * q.S, pcm_host + b0 * q.S, (size_t)nb * q.S * sizeof(float),
+                       cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->slice_ev[i], h->copy_stream));
+    CK(cudaStreamWaitEvent(s, h->slice_ev[i], 0));
+    KL(launch_mel_fft(k.pcm_stage + b0 * q.S, k.raw + b0 * q.T * q.n_mels, k.part + b0 * nblk * q.n_mels * 2, nb, q.S,
+                      q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, h->win, h->tw400, s, &h->launches,
+                      k.rag ? k.rag + b0 * RAG_STRIDE : nullptr));
+  }
+  KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
+  return VASR_OK;
+}
+
 int check_ready(const vasr_handle* h) {
   if (!h) return fail(VASR_ERR_INVALID, "null handle");
   if (!h->committed) return fail(VASR_ERR_STATE, "weights not committed (call vasr_commit_weights)");
@@ -804,6 +832,9 @@ int vasr_create(const vasr_config* cfg, int device, vasr_handle** out) {
   h->num_sms = prop.multiProcessorCount;
   h->prof = debug_env_int("VASR_PROF", 0);
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->slice_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->copy_gate, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->call_done, cudaEventDisableTiming));
   h->ev.resize(64);
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -826,6 +857,10 @@ void vasr_destroy(vasr_handle* h) {
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto& e : h->slice_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_gate) cudaEventDestroy(h->copy_gate);
   if (h->call_done) cudaEventDestroy(h->call_done);
   for (int i = 0; i < vasr_handle::RAG_RING; ++i) {
     if (h->rag_pin[i]) cudaFreeHost(h->rag_pin[i]);
@@ -1158,13 +1193,12 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
   RET(ensure_workspace(h, q, true, true, &k, host));
   if (sample_lens) RET(upload_ragged(h, q, k, sample_lens, true, s));
   if (host) {
-    CK(cudaMemcpyAsync(k.pcm_stage, pcm_host, (size_t)B * S * sizeof(float), cudaMemcpyHostToDevice, s));
-    pcm_dev = k.pcm_stage;
     tokens_dev = k.tok_stage;
     lens_dev = k.len_stage;
   }
   timing_begin(h, s);
-  RET(run_mel(h, q, k, pcm_dev, 1, s));
+  if (host) RET(run_mel_from_host(h, q, k, pcm_host, s));
+  else RET(run_mel(h, q, k, pcm_dev, 1, s));
   KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag));
   RET(run_model(h, q, k, k.logits, nullptr, nullptr, nullptr, s));
   KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));

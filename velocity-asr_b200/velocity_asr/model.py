@@ -5,7 +5,6 @@ import ctypes
 import os
 from typing import Dict, Iterable, Iterator, List, Optional, Tuple, Union
 
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -20,14 +19,10 @@ def _stream_ptr(device) -> ctypes.c_void_p:
 
 def _token_lists(tokens: torch.Tensor, lens: torch.Tensor) -> List[List[int]]:
     """(B, L) left-packed int32 ids + (B,) counts (host tensors) -> ragged Python lists."""
-    tok, counts = tokens.numpy(), lens.numpy()
-    # one boolean gather + one tolist for the whole batch, then list slices (no per-utterance numpy calls)
-    flat = tok[np.arange(tok.shape[1])[None, :] < counts[:, None]].tolist()
-    out, o = [], 0
-    for n in counts.tolist():
-        out.append(flat[o:o + n])
-        o += n
-    return out
+    # the cost is the creation of the Python ints themselves (~16 k per batch of 64 x 15 s: 0.5 ms); a masked
+    # gather + one tolist + slicing was measured slower than per-utterance tolist
+    tok = tokens.numpy()
+    return [tok[b, :n].tolist() for b, n in enumerate(lens.tolist())]
 
 
 def _lengths_tensor(lengths, B: int) -> torch.Tensor:
@@ -78,8 +73,8 @@ class _Engine:
         # the committed weights.  Contract: edits that bypass the version counter (p.data.copy_(), .data.mul_(),
         # EMA updates through .data) are NOT seen — call VELOCITYASR.refresh_weights() after such an edit.
         qp = tuple(sorted((act_qparams or {}).items())) if quantized else ()
-        fp = (quantized, qp) + tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in state.items())
-        fp += tuple((k, v.data_ptr(), v._version) for k, v in extra.items())
+        fp = (quantized, qp) + tuple((v.data_ptr(), v._version) for v in state.values())
+        fp += tuple((v.data_ptr(), v._version) for v in extra.values())
         if fp == self.fingerprint:
             return
         _native.check(self.lib.vasr_set_quantization(self.handle, int(quantized)))
@@ -129,6 +124,7 @@ class VELOCITYASR(nn.Module):
     def refresh_weights(self) -> None:
         """Forget the device copies of the weights: the next call re-uploads them.  Needed only after edits
         that bypass torch's version counter (p.data.copy_(), .data.mul_(), EMA through .data)."""
+        self.__dict__["_state_slots"] = None
         for eng in self._engines.values():
             eng.fingerprint = None
 
@@ -148,9 +144,21 @@ class VELOCITYASR(nn.Module):
             self._engines[idx] = eng
         from .audio import frontend_tables
         fb, win = frontend_tables(self.config.mel_bins)
-        # same keys and order as state_dict(), without the detach/copy work of building one per call
-        state = dict(self.named_parameters())
-        state.update({k: v for k, v in self.named_buffers() if k.split(".")[-1] not in self._non_persistent})
+        # Same keys and order as state_dict().  The walk over the module tree is cached as (key, owning dict, name)
+        # triples (208 tensors: 0.4 ms per call otherwise); the tensors themselves are looked up on every call, so a
+        # replaced Parameter object, .to() / .cuda() (new storage) and in-place edits (version counter) are all seen.
+        slots = self.__dict__.get("_state_slots")
+        if slots is None:
+            slots = []
+            for prefix, mod in self.named_modules():
+                dot = prefix + "." if prefix else ""
+                slots += [(dot + n, mod._parameters, n) for n, p in mod._parameters.items() if p is not None]
+            for prefix, mod in self.named_modules():
+                dot = prefix + "." if prefix else ""
+                slots += [(dot + n, mod._buffers, n) for n, b in mod._buffers.items()
+                          if b is not None and n not in mod._non_persistent_buffers_set]
+            self.__dict__["_state_slots"] = slots
+        state = {key: owner[name] for key, owner, name in slots}
         eng.sync_weights(state, {"frontend.mel_filterbank": fb, "frontend.window": win},
                          quantized=getattr(self, "_quantized", False), act_qparams=getattr(self, "_act_qparams", None))
         return eng
