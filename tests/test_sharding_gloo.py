@@ -34,6 +34,17 @@ def _worker(rank, world, port, n_items, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     audio = torch.arange(n_items, dtype=torch.float32).unsqueeze(1).repeat(1, 4) / 1000.0
     res = transcribe_sharded(_StubModel(), audio)
+    # the compact exchange: fixed-size token matrices to rank 0
+    from velocity_asr.sharding import gather_token_arrays
+    import numpy as np
+    tok = np.full((3, 5), rank + 1, dtype=np.int32)
+    cnt = np.array([rank, 2, 5], dtype=np.int32)
+    arr = gather_token_arrays(tok, cnt, dst=0)
+    if rank == 0:
+        assert arr[0].shape == (3 * world, 5) and arr[1].tolist() == [0, 2, 5, 1, 2, 5][:3 * world]
+        assert (arr[0][3:] == 2).all() and (arr[0][:3] == 1).all()
+    else:
+        assert arr is None
     out[rank] = (shard_range(n_items, rank, world), res)
     dist.barrier()
     dist.destroy_process_group()

@@ -265,13 +265,16 @@ class VELOCITYASR(nn.Module):
         return _token_lists(tokens, lens)
 
     @torch.no_grad()
-    def transcribe_batches(self, batches: Iterable[torch.Tensor]) -> Iterator[List[List[int]]]:
+    def transcribe_batches(self, batches: Iterable[torch.Tensor], as_arrays: bool = False
+                           ) -> Iterator[List[List[int]]]:
         """transcribe() over a stream of host batches, pipelined: while the kernels of batch i run,
         batch i+1 is copied host->device on a second stream and the token ids of batch i-1 are copied
         back and turned into lists.  Yields one List[List[int]] per input batch, in order; results
         are identical to calling transcribe() on each batch.  Batches are (B, S) float32 CPU
         tensors (pin them for full PCIe speed); shapes may change from batch to batch.  An item may also
-        be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths)."""
+        be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths).
+        as_arrays=True yields (tokens (B, L) int32 left-packed, counts (B,) int32) numpy copies instead of lists:
+        the compact form sharding.gather_token_arrays exchanges between ranks."""
         dev = self._exec_device()
         eng = self._engine(dev)
         comp = torch.cuda.current_stream(dev)
@@ -317,15 +320,17 @@ class VELOCITYASR(nn.Module):
             sl["lens_h"].copy_(sl["lens"], non_blocking=True)
             sl["done"].record(comp)
             if pending is not None:
-                yield self._collect(pending)
+                yield self._collect(pending, as_arrays)
             pending = sl
             i += 1
         if pending is not None:
-            yield self._collect(pending)
+            yield self._collect(pending, as_arrays)
 
     @staticmethod
-    def _collect(sl) -> List[List[int]]:
+    def _collect(sl, as_arrays: bool = False):
         sl["done"].synchronize()
+        if as_arrays:
+            return sl["tok_h"].numpy().copy(), sl["lens_h"].numpy().copy()
         return _token_lists(sl["tok_h"], sl["lens_h"])
 
     @torch.no_grad()
