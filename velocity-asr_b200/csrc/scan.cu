@@ -71,9 +71,10 @@ __device__ __forceinline__ void powers_generic(float s, const float (&al2)[SPL],
 // step at 8q touches the higher levels, which sit in local memory (one read, ~one write per 8 steps).
 //
 // Where the quirk stops costing anything.  Every term that enters hP[t] carries the factor exp(A S[t]), the decay
-// from time 0, and S only grows (dt is a softplus output, ssm.py:118).  Once min_n |A[n]| S[t] log2(e) >= 160 that
-// factor is exactly 0 in fp32 for every state (this kernel's ex2.approx.ftz and the reference's product of dA
-// alike), so hP[t] = hP[parent(t)] bit for bit from then on, and the true state H is never needed again:
+// from time 0, and S only grows (dt is a softplus output, ssm.py:118).  Once min_n |A[n]| S[t] log2(e) >= 127 that
+// factor is exactly 0 for every state in this kernel's arithmetic (ex2.approx.ftz flushes results below 2^-126;
+// the reference's fp32 product of dA is below 1e-38 there, i.e. invisible), so hP[t] = hP[parent(t)] bit for bit
+// from then on, and the true state H is never needed again:
 //   phase 1  (until every row of the CTA has passed that point, checked once per 16-step chunk): the full rule;
 //   phase 2  (from there to the next power of two P2): hP[t] = hP[parent(t)], y = <hP[t], C[t]> + x D — one FMA
 //            per state, no B, no dt;
@@ -85,10 +86,25 @@ __device__ __forceinline__ void powers_generic(float s, const float (&al2)[SPL],
 // dt stays small (sum of dt below ~110 over the utterance) runs phase 1 throughout.
 // ------------------------------------------------------------------------------------------
 constexpr int TCQ = 16;
-constexpr float QUIRK_DEAD_LOG2 = 160.0f;     // exp(A S) < 2^-160: zero in fp32, denormals included
+constexpr float QUIRK_DEAD_LOG2 = 127.0f;     // 2^-127: below the smallest normal fp32, ex2.approx.ftz returns exactly 0
 
 struct Anc {
   State8 hp, H;
+  double S;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// State of the narrow mode: two states per lane (one packed pair), see scan_quirk_kernel.
+struct Anc1 {
+  u64 hp, H;
   double S;
 };
 
@@ -100,12 +116,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   constexpr int NR = (LPR == 8) ? 3 : (LPR == 4 ? 2 : (LPR == 2 ? 1 : 0));
   constexpr int TPL = 8 >> NR;
   constexpr int HL = NLEV - 4;   // levels >= 4
+  constexpr int NN = 2 * LPR;    // states that stay in the narrow mode: 0 .. NN-1, two per lane
 
-  __shared__ __align__(16) float sB[TCQ][N];
-  __shared__ __align__(16) float sC[TCQ][N];
-  __shared__ float sx[TCQ][ROWS];
-  __shared__ float sdt[TCQ][ROWS];
-  __shared__ float sz[TCQ][ROWS];
+  // two stages: the tiles of chunk c + 1 travel (cp.async) while chunk c is computed.  B / C rows are stored in
+  // 16-byte pieces at permuted slots (piece f of a row at slot (f & 1) LPR + (f >> 1)) so that the 16-byte reads
+  // of the wide mode hit distinct banks; the narrow mode reads its two states out of the same layout.
+  __shared__ __align__(16) float sBs[2][TCQ][N];
+  __shared__ __align__(16) float sCs[2][TCQ][N];
+  __shared__ __align__(16) float sxs[2][TCQ][ROWS];
+  __shared__ __align__(16) float sdts[2][TCQ][ROWS];
+  __shared__ __align__(16) float szs[2][TCQ][ROWS];
   __shared__ float sy[TCQ][ROWS];
 
   const int tid = threadIdx.x;
@@ -128,6 +148,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
   for (int o = 1; o < LPR; o <<= 1) amin_l2 = fminf(amin_l2, __shfl_xor_sync(0xffffffffu, amin_l2, o));
   bool frozen = false;                        // phase 2: hP[t] = hP[parent(t)]
   int64_t t_zero = L;                         // phase 3 starts here (a power of two >= the start of phase 2)
+  // Narrow mode (structured A): the states decay in order, state n at the rate (n + 1).  Once exp(A[n] S) is an
+  // exact zero for every n >= NN in every row of the CTA, and the next power of two has passed (so that their
+  // hP is zero, not just frozen), only the NN slowest states are left: the CTA continues with two states per lane
+  // instead of eight.  With dt ~ 0.7 that is after the first 16 tokens.
+  int64_t t_narrow = L;
+  bool narrow_known = !STRUCT || N <= NN;
 
   Anc cur, a1, a2, a3;
 #pragma unroll
@@ -147,36 +173,121 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
     for (int k = 0; k < SPL; ++k) hi_hp[l][k] = hi_H[l][k] = 0.f;
   }
 
-  int64_t tc0 = 0;
-  for (; tc0 < L && tc0 < t_zero; tc0 += TCQ) {
-    if (tc0 + TCQ >= L) pdl_trigger();     // last chunk: see scan_seq_kernel
-    const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
-    for (int idx = tid; idx < TCQ * (N / 4); idx += SCAN_THREADS) {
-      const int t = idx / (N / 4), f = idx % (N / 4);
-      float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vc = vb;
-      if (t < tcn) {
-        const int64_t row = b * L + tc0 + t;
-        if (!frozen) vb = __ldg(reinterpret_cast<const float4*>(a.Bm + row * a.ldb + 4 * f));
-        vc = __ldg(reinterpret_cast<const float4*>(a.Cm + row * a.ldc + 4 * f));
+  // ---- pieces shared by the wide and the narrow chunk loop
+  // 16-byte cp.async needs 16-byte aligned rows everywhere; anything else is staged through registers, chunk by chunk
+  const bool async_ok = !((a.ldx | a.lddt | a.ldb | a.ldc | (gate ? a.ldz : 0)) & 3) &&
+                        !((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.dt) |
+                           reinterpret_cast<uintptr_t>(a.Bm) | reinterpret_cast<uintptr_t>(a.Cm) |
+                           (gate ? reinterpret_cast<uintptr_t>(a.z) : 0)) & 15);
+  // tiles of the chunk starting at t0 -> stage st.  nstates: how many leading states of B / C are wanted.
+  // Asynchronous form: always ends with a commit (an empty group past the end of the sequence).
+  auto load_chunk = [&](int64_t t0, int st, int nstates, bool async) {
+    const int tcn = t0 >= L ? 0 : (int)((L - t0) < TCQ ? (L - t0) : TCQ);
+    const int nf = nstates / 4;
+    for (int idx = tid; idx < TCQ * nf; idx += SCAN_THREADS) {
+      const int t = idx / nf, f = idx % nf;
+      if (t >= tcn) continue;
+      const int64_t row = b * L + t0 + t;
+      const int slot = (f & 1) * LPR + (f >> 1);
+      if (async) {
+        if (!frozen) cp_async16(&sBs[st][t][4 * slot], a.Bm + row * a.ldb + 4 * f);
+        cp_async16(&sCs[st][t][4 * slot], a.Cm + row * a.ldc + 4 * f);
+      } else {
+        float vb[4] = {0.f, 0.f, 0.f, 0.f}, vc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!frozen) vb[i] = __ldg(a.Bm + row * a.ldb + 4 * f + i);
+          vc[i] = __ldg(a.Cm + row * a.ldc + 4 * f + i);
+        }
+        *reinterpret_cast<float4*>(&sBs[st][t][4 * slot]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+        *reinterpret_cast<float4*>(&sCs[st][t][4 * slot]) = make_float4(vc[0], vc[1], vc[2], vc[3]);
       }
-      const int slot = (f & 1) * LPR + (f >> 1);   // conflict-free 16-byte phases (see below)
-      *reinterpret_cast<float4*>(&sB[t][4 * slot]) = vb;
-      *reinterpret_cast<float4*>(&sC[t][4 * slot]) = vc;
     }
-    for (int idx = tid; idx < TCQ * ROWS; idx += SCAN_THREADS) {
-      const int t = idx / ROWS, r = idx % ROWS;
-      float vx = 0.f, vd = 0.f, vz = 0.f;
-      if (t < tcn) {
-        const int64_t row = b * L + tc0 + t;
-        vx = __ldg(a.x + row * a.ldx + d0 + r);
-        if (!frozen) vd = __ldg(a.dt + row * a.lddt + d0 + r);
-        if (gate) vz = __ldg(a.z + row * a.ldz + d0 + r);
+    if (async) {
+      for (int idx = tid; idx < TCQ * (ROWS / 4); idx += SCAN_THREADS) {
+        const int t = idx / (ROWS / 4), r = 4 * (idx % (ROWS / 4));
+        if (t >= tcn) continue;
+        const int64_t row = b * L + t0 + t;
+        cp_async16(&sxs[st][t][r], a.x + row * a.ldx + d0 + r);
+        if (!frozen) cp_async16(&sdts[st][t][r], a.dt + row * a.lddt + d0 + r);
+        if (gate) cp_async16(&szs[st][t][r], a.z + row * a.ldz + d0 + r);
       }
-      sx[t][r] = vx;
-      sdt[t][r] = vd;
-      sz[t][r] = vz;
+      cp_async_commit();
+    } else {
+      for (int idx = tid; idx < TCQ * ROWS; idx += SCAN_THREADS) {
+        const int t = idx / ROWS, r = idx % ROWS;
+        if (t >= tcn) continue;
+        const int64_t row = b * L + t0 + t;
+        sxs[st][t][r] = __ldg(a.x + row * a.ldx + d0 + r);
+        if (!frozen) sdts[st][t][r] = __ldg(a.dt + row * a.lddt + d0 + r);
+        if (gate) szs[st][t][r] = __ldg(a.z + row * a.ldz + d0 + r);
+      }
+    }
+  };
+  // top of a chunk: request the next chunk's tiles, make this chunk's visible; returns this chunk's stage
+  auto begin_chunk = [&](int64_t tc0, int nstates) {
+    const int st = (int)((tc0 / TCQ) & 1);
+    if (async_ok) {
+      load_chunk(tc0 + TCQ, st ^ 1, nstates, true);   // everyone left that stage at the previous end_chunk barrier
+      cp_async_wait<1>();
+    } else {
+      load_chunk(tc0, st, nstates, false);
     }
     __syncthreads();
+    return st;
+  };
+  if (async_ok) load_chunk(0, 0, N, true);
+  auto reduce_gate = [&](float (&yp)[8], int g8, const float (*sx)[ROWS], const float (*sz)[ROWS]) {   // 8 steps' partial <hP, C> -> sy
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int lane_bit = LPR >> (r + 1);
+      const int cnt = 4 >> r;
+      const bool hi = (j & lane_bit) != 0;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) {
+        const float mine = hi ? yp[i + cnt] : yp[i];
+        const float other = hi ? yp[i] : yp[i + cnt];
+        yp[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TPL; ++i) {
+      const int t = g8 + j * TPL + i;
+      float yv = yp[i] + sx[t][rl] * Dd;
+      if (gate) {
+        const float zv = sz[t][rl];
+        yv *= zv / (1.0f + __expf(-zv));
+      }
+      sy[t][rl] = yv;
+    }
+  };
+  // end of a chunk: phase switch (has every row of the CTA decayed to an exact zero?) and the stores
+  auto end_chunk = [&](int64_t tc0, int tcn, double S_row) {
+    const bool dead = frozen || (float)S_row * amin_l2 >= QUIRK_DEAD_LOG2;
+    const bool all_dead = __syncthreads_and(dead) != 0;       // also orders sy before the stores below
+    if (all_dead && !frozen) {
+      frozen = true;
+      int64_t p2 = TCQ;
+      while (p2 < tc0 + TCQ) p2 <<= 1;
+      t_zero = p2;
+    }
+    for (int idx = tid; idx < tcn * ROWS; idx += SCAN_THREADS) {
+      const int t = idx / ROWS, r = idx % ROWS;
+      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
+    }
+  };
+
+  // =========================================================================== wide mode: 8 states per lane
+  int64_t tc0 = 0;
+  for (; tc0 < L && tc0 < t_zero && tc0 < t_narrow; tc0 += TCQ) {
+    if (tc0 + TCQ >= L) pdl_trigger();     // last chunk: see scan_seq_kernel
+    const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
+    const int st = begin_chunk(tc0, N);
+    float (*sB)[N] = sBs[st];
+    float (*sC)[N] = sCs[st];
+    float (*sx)[ROWS] = sxs[st];
+    float (*sdt)[ROWS] = sdts[st];
+    float (*sz)[ROWS] = szs[st];
 
 #pragma unroll 1
     for (int g8 = 0; g8 < TCQ; g8 += 8) {
@@ -185,8 +296,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
       // one step: hP from `par`, output partial, then the true-recurrence update of cur.H / cur.S
       auto step = [&](int i, const Anc& par, bool has_parent) {
         const int t = g8 + i;
-        const float dtv = sdt[t][rl];
-        const float xv = sx[t][rl];
         const ulonglong2 c01 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * j]);
         const ulonglong2 c23 = *reinterpret_cast<const ulonglong2*>(&sC[t][4 * (LPR + j)]);
         if (has_parent && frozen) {
@@ -270,44 +379,114 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
       step(5, a1, true); advance(5);
       step(6, a2, true); a1 = cur; advance(6);
       step(7, a1, true); advance(7);
+      reduce_gate(yp, g8, sx, sz);
+    }
+    if (!narrow_known && !frozen) {          // are the states >= NN exact zeros in every row from here on?
+      const bool hi_dead = (float)cur.S * ((float)(NN + 1) * LOG2E) >= QUIRK_DEAD_LOG2;
+      if (__syncthreads_and(hi_dead)) {
+        narrow_known = true;
+        int64_t p2 = TCQ;
+        while (p2 < tc0 + TCQ) p2 <<= 1;
+        t_narrow = p2;
+      }
+    }
+    end_chunk(tc0, tcn, cur.S);
+  }
 
+  // =========================================================================== narrow mode: 2 states per lane
+  if (STRUCT && tc0 < L && tc0 < t_zero && !frozen) {
+    // states 2 j, 2 j + 1 of the row: pair (j % 4) of the lane that held states 8 (j / 4) ...; S is shared.
+    // Ancestors: tc0 is a power of two, so every index from here on has its ancestors at or after tc0, or at 0
+    // (state zero): the saved levels start again from zero, only the true state and S carry over.
+    Anc1 c1, b1, b2, b3;
+    {
+      const int src = (tid & 31) - j + (j >> 2);
+      u64 mine = 0ull;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const int lane_bit = LPR >> (r + 1);
-        const int cnt = 4 >> r;
-        const bool hi = (j & lane_bit) != 0;
-#pragma unroll
-        for (int i = 0; i < cnt; ++i) {
-          const float mine = hi ? yp[i + cnt] : yp[i];
-          const float other = hi ? yp[i] : yp[i + cnt];
-          yp[i] = mine + __shfl_xor_sync(0xffffffffu, other, lane_bit);
-        }
+      for (int k = 0; k < 4; ++k) {
+        const u64 v = __shfl_sync(0xffffffffu, cur.H.v[k], src);
+        if (k == (j & 3)) mine = v;
       }
-#pragma unroll
-      for (int i = 0; i < TPL; ++i) {
-        const int t = g8 + j * TPL + i;
-        float yv = yp[i] + sx[t][rl] * Dd;
-        if (gate) {
-          const float zv = sz[t][rl];
-          yv *= zv / (1.0f + __expf(-zv));
+      c1.H = mine;
+      c1.hp = 0ull;
+      c1.S = cur.S;
+      b1 = b2 = b3 = c1;
+    }
+    for (int l = 0; l < hl_used; ++l) {
+      hi_S[l] = 0.0;
+      hi_hp[l][0] = hi_hp[l][1] = hi_H[l][0] = hi_H[l][1] = 0.f;
+    }
+    const float e_mul = (float)(2 * j + 1);
+    auto pw = [&](float s) {                 // (r^(2j+1), r^(2j+2)), r = 2^s
+      const float r1 = ex2_approx(s);
+      const float e1 = ex2_approx(s * e_mul);
+      return pack2(e1, e1 * r1);
+    };
+    for (; tc0 < L && tc0 < t_zero; tc0 += TCQ) {
+      if (tc0 + TCQ >= L) pdl_trigger();
+      const int tcn = (int)((L - tc0) < TCQ ? (L - tc0) : TCQ);
+      const int st = begin_chunk(tc0, NN);             // only the first NN states of B / C travel from here on
+      float (*sB)[N] = sBs[st];
+      float (*sC)[N] = sCs[st];
+      float (*sx)[ROWS] = sxs[st];
+      float (*sdt)[ROWS] = sdts[st];
+      float (*sz)[ROWS] = szs[st];
+      // states 2 j, 2 j + 1 inside the permuted 16-byte pieces: piece j / 2, second half for odd j
+      const int nsl = 4 * (((j >> 1) & 1) * LPR + (j >> 2)) + 2 * (j & 1);
+#pragma unroll 1
+      for (int g8 = 0; g8 < TCQ; g8 += 8) {
+        if (g8 >= tcn) break;
+        float yp[8];
+        auto step = [&](int i, const Anc1& par) {
+          const int t = g8 + i;
+          if (frozen) {
+            c1.hp = par.hp;
+          } else {
+            const u64 q = pw(-(float)c1.S * LOG2E);
+            const u64 pd = pw(-(float)(c1.S - par.S) * LOG2E);
+            const u64 inner = fma2(mul2(pd, pack2(-1.f, -1.f)), par.H, c1.H);
+            c1.hp = fma2(q, inner, par.hp);
+          }
+          yp[i] = hsum2(mul2(c1.hp, *reinterpret_cast<const u64*>(&sC[t][nsl])));
+        };
+        auto advance = [&](int i) {
+          if (frozen) return;
+          const int t = g8 + i;
+          const float dtv = sdt[t][rl];
+          const float u = sx[t][rl] * dtv;
+          c1.H = fma2(pw(-dtv * LOG2E), c1.H, mul2(pack2(u, u), *reinterpret_cast<const u64*>(&sB[t][nsl])));
+          c1.S += (double)dtv;
+        };
+        {
+          const int64_t tg = tc0 + g8;                 // > 0 here
+          const int z = 3 + (__ffsll((long long)(tg >> 3)) - 1);
+          const int pl = z + 1 - 4;
+          Anc1 par;
+          par.S = hi_S[pl];
+          par.hp = pack2(hi_hp[pl][0], hi_hp[pl][1]);
+          par.H = pack2(hi_H[pl][0], hi_H[pl][1]);
+          step(0, par);
+          for (int l = 4; l <= z; ++l) {
+            hi_S[l - 4] = c1.S;
+            unpack2(c1.hp, hi_hp[l - 4][0], hi_hp[l - 4][1]);
+            unpack2(c1.H, hi_H[l - 4][0], hi_H[l - 4][1]);
+          }
+          b1 = b2 = b3 = c1;
+          advance(0);
         }
-        sy[t][rl] = yv;
+        step(1, b1); advance(1);
+        step(2, b2); b1 = c1; advance(2);
+        step(3, b1); advance(3);
+        step(4, b3); b1 = b2 = c1; advance(4);
+        step(5, b1); advance(5);
+        step(6, b2); b1 = c1; advance(6);
+        step(7, b1); advance(7);
+        reduce_gate(yp, g8, sx, sz);
       }
-    }
-    // phase switch, once per chunk: has every row of the CTA decayed to an exact zero?
-    const bool dead = frozen || (float)cur.S * amin_l2 >= QUIRK_DEAD_LOG2;
-    const bool all_dead = __syncthreads_and(dead) != 0;       // also orders sy before the stores below
-    if (all_dead && !frozen) {
-      frozen = true;
-      int64_t p2 = TCQ;
-      while (p2 < tc0 + TCQ) p2 <<= 1;
-      t_zero = p2;
-    }
-    for (int idx = tid; idx < tcn * ROWS; idx += SCAN_THREADS) {
-      const int t = idx / ROWS, r = idx % ROWS;
-      a.y[(b * L + tc0 + t) * a.ldy + d0 + r] = sy[t][r];
+      end_chunk(tc0, tcn, c1.S);
     }
   }
+  cp_async_wait<0>();                       // a tile requested ahead may still be in flight
   // phase 3: hP = 0 for every remaining t, y = x D (gated)
   if (tc0 < L) {
     pdl_trigger();
@@ -379,15 +558,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
 //     bytes per timestep per warp).
 // ------------------------------------------------------------------------------------------
 constexpr int TCH = 16;   // timesteps per staged chunk
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1, 2 or 3)
 __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
