@@ -29,5 +29,7 @@ for _ in range(n):
     res = va.ctc_beam_search(lg, beam_width=a.width)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
-print(f"beam search B={a.batch} L={a.frames} V={a.vocab} W={a.width}: {dt * 1e3:.2f} ms per batch "
-      f"(host lists included), best-beam len {len(res[0][0].tokens)}")
+import json
+print(json.dumps({"what": "ctc_beam_search on the device, host result lists included", "batch": a.batch,
+                  "frames": a.frames, "vocab": a.vocab, "beam_width": a.width, "ms_per_batch": round(dt * 1e3, 3),
+                  "best_beam_len": len(res[0][0].tokens)}))

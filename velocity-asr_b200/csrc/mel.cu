@@ -108,11 +108,22 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
   const int nfr = (int)((Tb - t0) < FPC ? (Tb - t0) : FPC);   // frames of this CTA that exist
   const float* xb = pcm + b * S;
   const int nsamp = NHOP * (nfr - 1) + NFFT;
-  for (int i = tid; i < nsamp; i += MEL_WARPS * 32) {
-    int64_t g = t0 * NHOP + i - NPAD;           // index into the unpadded signal
-    if (g < 0) g = -g;                          // reflect without repeating the edge sample (audio.py:100-101)
-    if (g >= Sb) g = 2 * (Sb - 1) - g;
-    s_x[i] = (g >= 0 && g < Sb) ? __ldg(xb + g) : 0.f;
+  // The samples of the CTA's frames: contiguous in the signal except where the reflect padding folds them back at
+  // either end of the utterance (audio.py:100-101).  Interior CTAs — all but the first and the last one or two of an
+  // utterance — copy them as 16-byte vectors (the window start (t0 * 160 - 200) * 4 B is a multiple of 16 whenever
+  // the utterance's row is: S % 4 == 0).
+  const int64_t g0 = t0 * NHOP - NPAD;
+  if (g0 >= 0 && g0 + nsamp <= Sb && ((reinterpret_cast<uintptr_t>(xb + g0) & 15) == 0) && (nsamp & 3) == 0) {
+    const float4* src = reinterpret_cast<const float4*>(xb + g0);
+    float4* dst = reinterpret_cast<float4*>(s_x);
+    for (int i = tid; i < nsamp / 4; i += MEL_WARPS * 32) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < nsamp; i += MEL_WARPS * 32) {
+      int64_t g = g0 + i;                         // index into the unpadded signal
+      if (g < 0) g = -g;                          // reflect without repeating the edge sample
+      if (g >= Sb) g = 2 * (Sb - 1) - g;
+      s_x[i] = (g >= 0 && g < Sb) ? __ldg(xb + g) : 0.f;
+    }
   }
   for (int i = tid; i < NFFT; i += MEL_WARPS * 32) {
     s_win[i] = __ldg(win + i);

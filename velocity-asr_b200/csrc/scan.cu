@@ -536,7 +536,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Fast path of the true recurrence (scan_mode sequential / mamba).
+// True recurrence (scan_mode sequential / mamba) for what scan_rp_kernel below does not take: a trained model's
+// unstructured A (one ex2 per state), N = 32 / 16, rows that are not 16-byte aligned for its row-pair loads.  It was
+// the kernel of every shape until round 2; its structure is the base of scan_rp_kernel.
 //
 // ncu on the previous version (8 states per lane, register-staged tiles): 115 issued instructions
 // per warp-step against 32 packed state operations — index arithmetic of the staging code, the
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_quirk_kernel(ScanArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int TCH = 16;   // timesteps per staged chunk
 
-template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (1, 2 or 3)
+template <int LPR, int WARPS, int RPL, bool STRUCT>   // RPL = rows per lane (2 in every instantiation that is built)
 __global__ void __launch_bounds__(WARPS * 32, (RPL == 3 ? 256 : RPL == 2 ? 384 : 640) / (WARPS * 32)) scan_seq_kernel(ScanArgs a) {
   pdl_wait();
   constexpr int N = LPR * 16;
@@ -1460,7 +1462,7 @@ cudaError_t launch_seq(const ScanArgs& a, cudaStream_t s) {
   return e;
 }
 
-// picks the CTA shape: rows per CTA must divide Di.  (-DVASR_DEBUG builds: VASR_SCAN_RPL=1|2|3 overrides rows per lane.)
+// CTA shape of scan_seq_kernel: two rows per lane, 64 or 128 rows per CTA (Di is a multiple of 64: include/vasr.h).
 template <int LPR>
 cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
   constexpr int G = 32 / LPR;
@@ -1469,25 +1471,11 @@ cudaError_t launch_recurrence(const ScanArgs& a, cudaStream_t s) {
   if ((a.ldx & 3) || (a.lddt & 3) || (a.ldy & 1) || !al16(a.x) || !al16(a.dt) || (a.z && ((a.ldz & 3) || !al16(a.z))) ||
       (reinterpret_cast<uintptr_t>(a.y) & 7))
     return cudaErrorInvalidValue;
-  static const int rpl_env = debug_env_int("VASR_SCAN_RPL", 0);
-  const int rpl = rpl_env >= 1 && rpl_env <= 3 ? rpl_env : 2;
-  static const int warps_env = debug_env_int("VASR_SCAN_WARPS", 0);
-  if constexpr (LPR == 4) {
-    if (rpl == 3 && a.Di % (4 * G * 3) == 0) return launch_seq<LPR, 4, 3>(a, s);
-  }
-  if (rpl >= 2) {
-    // four warps = one warp of the CTA per SM sub-partition: the warps of a CTA then advance at the
-    // same rate and the per-chunk barrier costs nothing (measured 0.320 ms vs 0.356 ms with three)
-    if (LPR == 4 && warps_env != 3 && a.Di % (4 * G * 2) == 0) return launch_seq<LPR, 4, 2>(a, s);
-    if (LPR == 4 && a.Di % (3 * G * 2) == 0) return launch_seq<LPR, 3, 2>(a, s);
-    if (a.Di % (2 * G * 2) == 0 && 2 * G * 2 <= 128) return launch_seq<LPR, 2, 2>(a, s);
-    if (a.Di % (G * 2) == 0) return launch_seq<LPR, 1, 2>(a, s);
-  }
-  if (LPR == 4 && a.Di % (6 * G) == 0) return launch_seq<LPR, 6, 1>(a, s);
-  if (LPR == 4 && a.Di % (3 * G) == 0) return launch_seq<LPR, 3, 1>(a, s);
-  if (a.Di % (4 * G) == 0 && 4 * G <= 128) return launch_seq<LPR, 4, 1>(a, s);
-  if (a.Di % (2 * G) == 0 && 2 * G <= 128) return launch_seq<LPR, 2, 1>(a, s);
-  if (a.Di % G == 0) return launch_seq<LPR, 1, 1>(a, s);
+  // four warps = one warp of the CTA per SM sub-partition: the warps of a CTA then advance at the same rate and the
+  // per-chunk barrier costs nothing (measured 0.320 ms vs 0.356 ms with three)
+  if (4 * G * 2 <= 128 && a.Di % (4 * G * 2) == 0) return launch_seq<LPR, 4, 2>(a, s);
+  if (2 * G * 2 <= 128 && a.Di % (2 * G * 2) == 0) return launch_seq<LPR, 2, 2>(a, s);
+  if (a.Di % (G * 2) == 0) return launch_seq<LPR, 1, 2>(a, s);
   return cudaErrorInvalidValue;
 }
 
