@@ -782,6 +782,47 @@ def test_ctc_greedy_random_vs_oracle(va):
     assert va.ctc_greedy_decode(lg.cuda(), blank_token=2) == O.ctc_greedy_decode(lg.numpy(), blank_token=2)
 
 
+def test_non_default_local_stack_config(va):
+    """ssm_kernel_size 3, expand_ratio 1, 3 layers of state 32 in the local stack; the global stack keeps the
+    reference's hard-coded expand_ratio 2 / kernel_size 4 (ssm.py:529-538).  Against the oracle, both scan modes."""
+    for mode in ("sequential", "parallel"):
+        torch.manual_seed(21)
+        m = va.VELOCITYASR(va.VelocityASRConfig(ssm_layers=3, ssm_state_dim=32, ssm_expand_ratio=1,
+                                                ssm_kernel_size=3, scan_mode=mode))
+        m.load_state_dict(FU.amplify_state_dict(m.state_dict(), seed=4))
+        m = m.cuda().eval()
+        audio = FU.synth_audio(2, 12000, seed=8)
+        mel = va.compute_mel_spectrogram(audio.cuda())
+        got = m(mel)
+        want = O.forward(mel.double().cpu().numpy(), np_sd(m),
+                         dict(ssm_layers=3, ssm_state_dim=32, ssm_expand_ratio=1, ssm_kernel_size=3, scan_mode=mode))
+        assert rel(got, want) < LOGIT_RTOL
+        assert m.transcribe(audio.cuda()) == va.ctc_greedy_decode(got)
+    with pytest.raises(NotImplementedError):
+        va.VELOCITYASR(va.VelocityASRConfig(attention_heads=8, attention_dim=64)).cuda()(mel)   # > 4 heads
+
+
+def test_calls_on_one_handle_are_ordered_across_streams(va):
+    """An asynchronous forward on the caller's stream followed at once by a host-tensor transcribe (which runs on the
+    handle's own stream) share the workspace: the second call must wait for the first on the device."""
+    m = make_model(va, "sequential", amp=True)
+    audio = FU.synth_audio(8, 48000, seed=3)
+    mel = va.compute_mel_spectrogram(audio.cuda())
+    want_logits = m(mel).clone()
+    want_tokens = m.transcribe(audio.cuda())
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(5):
+        with torch.cuda.stream(side):
+            logits = m(mel)                        # queued on `side`, not waited for
+        tokens = m.transcribe(audio)               # CPU tensor -> the handle's own stream
+        side.synchronize()
+        assert torch.equal(logits, want_logits)
+        assert tokens == want_tokens
+    # the device a call runs on is restored afterwards
+    assert torch.cuda.current_device() == 0
+
+
 # ------------------------------------------------------------------ errors ---------------
 def test_error_behaviour(va):
     with pytest.raises(ValueError):

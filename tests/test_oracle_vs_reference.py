@@ -78,3 +78,30 @@ def test_beam_search_matches_reference():
         lp = torch.log_softmax(torch.from_numpy(lg), dim=-1).numpy()
         got = O.ctc_beam_search(lg, W, blank, log_probs=lp)
         assert [[(d.tokens, d.score) for d in utt] for utt in ref] == got
+
+
+def test_non_default_local_stack_shapes():
+    """A config whose LOCAL stack differs from the global one (ssm_kernel_size 3, expand_ratio 1, 3 layers, state 32):
+    GlobalSSM keeps expand_ratio 2 / kernel_size 4 whatever the config says (ssm.py:529-538).  The product's parameter
+    tree must draw the same tensors as the reference and the oracle (shape-driven) must follow it."""
+    import velocity_asr
+    kw = dict(ssm_layers=3, ssm_state_dim=32, ssm_expand_ratio=1, ssm_kernel_size=3, scan_mode="sequential")
+    torch.manual_seed(21)
+    ref = R.VELOCITYASR(R.VelocityASRConfig(**kw)).eval()
+    torch.manual_seed(21)
+    ours = velocity_asr.VELOCITYASR(velocity_asr.VelocityASRConfig(**kw))
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    assert a["local_ssm.layers.0.conv.weight"].shape[-1] == 3
+    assert a["global_context.global_ssm.layers.0.conv.weight"].shape[-1] == 4
+    assert a["global_context.global_ssm.layers.0.ssm.in_proj.weight"].shape[0] == 2 * 2 * 192
+    sd = FU.amplify_state_dict(a, seed=4)
+    ref.load_state_dict(sd)
+    audio = FU.synth_audio(2, 12000, seed=8)
+    with torch.no_grad():
+        mel = R.compute_mel_spectrogram(audio)
+        want = ref(mel).numpy()
+    got = O.forward(mel.numpy(), {k: v.numpy() for k, v in sd.items()}, dict(kw))
+    assert rel(got, want) < 5e-5
