@@ -1427,7 +1427,8 @@ cudaError_t launch_rp_cfg(const ScanArgs& a, int sms, cudaStream_t s) {
     sa.n_slots = (int)slots;
     sa.flags = reinterpret_cast<unsigned int*>(sc->mem);
     sa.state = reinterpret_cast<u64*>(reinterpret_cast<char*>(sc->mem) + 4096);
-    sa.epoch = ++sc->epoch;
+    if (++sc->epoch == 0) ++sc->epoch;              // 0 is what the zeroed flags hold
+    sa.epoch = sc->epoch;
     grid = (unsigned)slots;
     smem = SPLIT_SMEM;
   }
