@@ -42,17 +42,38 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
 // one warp per utterance: keep[t] = pred[t] != blank && (!collapse || t == 0 || pred[t] != pred[t-1]).
 // (A blank resets the reference's `prev`, and a blank predecessor differs from any kept token,
 // so comparing with the raw predecessor is the same rule, decode.py:55-66.)
-__global__ void __launch_bounds__(32) ctc_collapse_kernel(const int32_t* __restrict__ pred,
+// PARTS (256 threads): the frames' predictions are first taken from the per-slot (max, first argmax) pairs the
+// CTC-head projection left (GemmArgs::amax_val) — the best over the slots in column order, a later slot only on a
+// strictly greater value, i.e. ties -> lowest index as torch.argmax (decode.py:46) — and written to `pred`; warp 0
+// then collapses as usual.
+template <bool PARTS>
+__global__ void __launch_bounds__(PARTS ? 256 : 32) ctc_collapse_kernel(int32_t* pred,
                                                           int32_t* __restrict__ tokens, int32_t* __restrict__ lens,
                                                           int64_t L, int blank, int collapse,
-                                                          const int32_t* __restrict__ rag) {
+                                                          const int32_t* __restrict__ rag,
+                                                          const float* __restrict__ pv, const int32_t* __restrict__ pi,
+                                                          int slots, int64_t M) {
   pdl_trigger();
   pdl_wait();
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x;
-  const int32_t* p = pred + b * L;
+  int32_t* p = pred + b * L;
   int32_t* out = tokens + b * L;
   const int64_t Lb = rag ? rag[b * RAG_STRIDE + RAG_L] : L;   // ragged: tokens past the utterance's end are padding
+  if (PARTS) {
+    for (int64_t t = threadIdx.x; t < Lb; t += 256) {
+      float best = -INFINITY;
+      int bi = -1;
+      for (int s = 0; s < slots; ++s) {
+        const int i = pi[(int64_t)s * M + b * L + t];
+        const float v = pv[(int64_t)s * M + b * L + t];
+        if (i >= 0 && (v > best || bi < 0)) { best = v; bi = i; }
+      }
+      p[t] = bi < 0 ? 0 : bi;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+  }
   int count = 0;
   for (int64_t t0 = 0; t0 < Lb; t0 += 32) {
     const int64_t t = t0 + lane;
@@ -126,10 +147,15 @@ cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, 
   return e;
 }
 
-cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
-                                int blank, int collapse, cudaStream_t s, int64_t* launches, const int32_t* rag) {
+cudaError_t launch_ctc_collapse(int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
+                                int blank, int collapse, cudaStream_t s, int64_t* launches, const int32_t* rag,
+                                const float* amax_val, const int32_t* amax_idx, int slots) {
   if (B <= 0) return cudaSuccess;
-  const cudaError_t e = launch_k(ctc_collapse_kernel, dim3((unsigned)B), dim3(32), 0, s, pred, tokens, lens, L, blank, collapse, rag);
+  const cudaError_t e =
+      amax_val ? launch_k(ctc_collapse_kernel<true>, dim3((unsigned)B), dim3(256), 0, s, pred, tokens, lens, L, blank,
+                          collapse, rag, amax_val, amax_idx, slots, B * L)
+               : launch_k(ctc_collapse_kernel<false>, dim3((unsigned)B), dim3(32), 0, s, pred, tokens, lens, L, blank,
+                          collapse, rag, amax_val, amax_idx, 0, B * L);
   if (launches) ++*launches;
   return e;
 }

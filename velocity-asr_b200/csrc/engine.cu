@@ -44,6 +44,7 @@ constexpr int N_FFT = 400, HOP = 160, N_FREQ = 201, PAD = 200;
 struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *conv_w, *conv_b, *A, *D;
   float *w_in, *w_xdt, *b_xdt, *w_out, *w_f1, *b_f1, *w_f2, *b_f2;
+  float* s_f1;             // norm2 is folded into ffn.0 (fold_ln): column sums of the folded weight
   int N = 0;
   int di = 0, ks = 0;      // d_inner and depthwise kernel size of THIS stack (GlobalSSM hard-codes 2 / 4: ssm.py:529-538)
   int structured = 0;
@@ -108,6 +109,11 @@ struct vasr_handle {
   float *w_q = nullptr, *b_q = nullptr, *w_kv = nullptr, *b_kv = nullptr, *w_o = nullptr, *b_o = nullptr;
   float *w_f3 = nullptr, *b_f3 = nullptr, *w_fo = nullptr, *b_fo = nullptr;
   float *ctc_g = nullptr, *ctc_b = nullptr, *w_ctc = nullptr, *b_ctc = nullptr;
+  // fp32 model only (the FakeQuantize model keeps its modules one by one, quantize.py:269-322): LayerNorms folded
+  // into the projection that follows them (fold_ln), and the fusion's stacked projection with its rows permuted for
+  // the gate epilogue (gate_perm_row)
+  float *w_q_ln = nullptr, *b_q_ln = nullptr, *s_q = nullptr, *w_kv_ln = nullptr, *b_kv_ln = nullptr, *s_kv = nullptr;
+  float *w_ctc_ln = nullptr, *b_ctc_ln = nullptr, *s_ctc = nullptr, *w_f3p = nullptr, *b_f3p = nullptr;
   float* win = nullptr;      // analysis window (400)
   float* tw400 = nullptr;    // W400^m = (cos, -sin)(2 pi m / 400)
   int *fb_lo = nullptr, *fb_off = nullptr;
@@ -185,6 +191,9 @@ struct Work {
   float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
   float *ga, *gb, *g2, *g2n, *kv;
   float* logits;
+  float* lnstat;         // (M, 2) row statistics of a projection with a folded LayerNorm
+  float* amax_val;       // argmax partials of the CTC head (argmax_slots(V) x M), greedy decode without logits
+  int32_t* amax_idx;
   int32_t* pred;
   float* pcm_stage;      // device copies for the *_host entry points
   int32_t *tok_stage, *len_stage;
@@ -225,6 +234,9 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   t.g2n = a.take<float>(q.M2 * q.d);
   t.kv = a.take<float>(q.M2 * 2 * q.att);
   if (need_logits) t.logits = a.take<float>(q.M * q.V);
+  t.lnstat = a.take<float>(q.M * 2);
+  t.amax_val = a.take<float>(q.M * argmax_slots(q.V));
+  t.amax_idx = a.take<int32_t>(q.M * argmax_slots(q.V));
   if (h->quant_active) t.qscratch = a.take<float>(q.M * (q.V > 3 * q.d ? q.V : 3 * q.d));
   t.pred = a.take<int32_t>(q.M);
   t.ragbuf = a.take<int32_t>(q.B * RAG_STRIDE);
@@ -322,6 +334,47 @@ int up_w(vasr_handle* h, const std::string& k, int64_t numel, int64_t rows, floa
   return upload(h, w.data(), w.size(), dst);
 }
 
+// y = Linear(LayerNorm(x)) = rstd * (x W'^T) - mean * rstd * s + b'   with   W' = W diag(gamma),
+// b' = b + W beta,  s[n] = sum_k W'[n, k]:  the projection kernel takes x itself, its converter threads gather
+// (mean, rstd) of the row they own and the epilogue applies the rest (GemmArgs::ln_s).  W: (N, K).
+void fold_ln(const std::vector<float>& W, int64_t N, int64_t K, const float* bias, const float* gamma,
+             const float* beta, std::vector<float>* Wf, std::vector<float>* bf, std::vector<float>* sf) {
+  Wf->resize((size_t)N * K);
+  bf->resize((size_t)N);
+  sf->resize((size_t)N);
+  for (int64_t n = 0; n < N; ++n) {
+    double sb = bias ? (double)bias[n] : 0.0, ss = 0.0;
+    for (int64_t k = 0; k < K; ++k) {
+      const float w = W[(size_t)n * K + k];
+      const float wf = w * gamma[k];
+      (*Wf)[(size_t)n * K + k] = wf;
+      sb += (double)w * (double)beta[k];
+      ss += (double)wf;
+    }
+    (*bf)[(size_t)n] = (float)sb;
+    (*sf)[(size_t)n] = (float)ss;
+  }
+}
+int upload_folded(vasr_handle* h, const std::vector<float>& W, int64_t N, int64_t K, const float* bias,
+                  const std::string& gk, const std::string& bk, float** Wd, float** bd, float** sd) {
+  const std::vector<float>*g, *b;
+  RET(need(h, gk, K, &g));
+  RET(need(h, bk, K, &b));
+  std::vector<float> Wf, bf, sf;
+  fold_ln(W, N, K, bias, g->data(), b->data(), &Wf, &bf, &sf);
+  RET(upload(h, Wf.data(), Wf.size(), Wd));
+  RET(upload(h, bf.data(), bf.size(), bd));
+  return upload(h, sf.data(), sf.size(), sd);
+}
+
+// Row r' of the permuted fusion projection (3 C rows: gate | local | global stacked): the 192-column tile t holds,
+// for its two 32-channel halves a, the chunks gate | local | global of channels 64 t + 32 a .. + 31, so that one
+// epilogue warp (three chunks) has everything the mix of its 32 channels needs.
+int gate_perm_row(int rp, int C) {
+  const int t = rp / 192, a = (rp % 192) / 96, j = (rp % 96) / 32, i = rp % 32;
+  return j * C + 64 * t + 32 * a + i;
+}
+
 int pack_block(vasr_handle* h, const std::string& p, int N, int expand, int ks, BlockW* w) {
   const int d = h->cfg.d_model, di = d * expand;
   w->N = N;
@@ -355,8 +408,10 @@ int pack_block(vasr_handle* h, const std::string& p, int N, int expand, int ks, 
   RET(upload(h, wx.data(), wx.size(), &w->w_xdt));
   RET(upload(h, bx.data(), bx.size(), &w->b_xdt));
   RET(up(h, p + "ssm.out_proj.weight", (int64_t)d * di, &w->w_out));
-  RET(up(h, p + "ffn.0.weight", (int64_t)di * d, &w->w_f1));
-  RET(up(h, p + "ffn.0.bias", di, &w->b_f1));
+  const std::vector<float>*f1w, *f1b;
+  RET(need(h, p + "ffn.0.weight", (int64_t)di * d, &f1w));
+  RET(need(h, p + "ffn.0.bias", di, &f1b));
+  RET(upload_folded(h, *f1w, di, d, f1b->data(), p + "norm2.weight", p + "norm2.bias", &w->w_f1, &w->b_f1, &w->s_f1));
   RET(up(h, p + "ffn.3.weight", (int64_t)d * di, &w->w_f2));
   RET(up(h, p + "ffn.3.bias", d, &w->b_f2));
   return VASR_OK;
@@ -552,6 +607,15 @@ int linear(vasr_handle* h, const float* A, int64_t lda, const float* W, const fl
   g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = act_from; g.resid = resid; g.ldr = ldr;
   return gemm_q(h, g, site, qscratch, s);
 }
+// Linear(LayerNorm(A rows)) with the LayerNorm folded into the projection (fold_ln): W, bias, colsum are the folded set
+int linear_ln(vasr_handle* h, const Work& k, const float* A, int64_t lda, const float* W, const float* bias,
+              const float* colsum, float* C, int64_t ldc, int64_t M, int64_t K, int64_t N, int act, cudaStream_t s) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.act = act; g.act_from = 0;
+  g.ln_s = colsum; g.ln_stats = k.lnstat;
+  return gemm(h, g, s);
+}
 
 
 int run_scan(vasr_handle* h, const BlockW& w, const Work& k, int64_t B, int64_t L, int quirk, cudaStream_t s) {
@@ -590,8 +654,7 @@ int run_block(vasr_handle* h, const BlockW& w, const Work& k, float* x, float* x
              nullptr, 0, s));
   RET(run_scan(h, w, k, B, L, quirk, s));
   RET(linear(h, k.yg, di, w.w_out, nullptr, x1, d, M, di, d, ACT_NONE, 0, x, d, s));
-  KL(launch_layer_norm(x1, d, k.u, d, w.ln2_g, w.ln2_b, M, d, s, &h->launches));
-  RET(linear(h, k.u, d, w.w_f1, w.b_f1, k.hbuf, di, M, d, di, ACT_GELU, 0, nullptr, 0, s));
+  RET(linear_ln(h, k, x1, d, w.w_f1, w.b_f1, w.s_f1, k.hbuf, di, M, d, di, ACT_GELU, s));    // norm2 folded into ffn.0
   RET(linear(h, k.hbuf, di, w.w_f2, w.b_f2, x, d, M, di, d, ACT_NONE, 0, x1, d, s));
   return VASR_OK;
 }
@@ -611,20 +674,42 @@ int run_global_context(vasr_handle* h, const Dims& q, const Work& k, cudaStream_
   KL(launch_layer_norm(k.ga, d, k.ga, d, h->glo_g, h->glo_b, q.Mg, d, s, &h->launches));
   KL(launch_adaptive_pool(k.ga, d, k.g2, q.B, q.K1, q.K2, d, s, &h->launches, k.rag, RAG_K1, RAG_K2));
   RET(linear(h, k.g2, d, h->p2_w, h->p2_b, k.g2n, d, q.M2, d, d, ACT_NONE, 0, nullptr, 0, s, Q_P2, k.qscratch));
-  KL(launch_layer_norm(k.g2n, d, k.g2n, d, h->n1_g, h->n1_b, q.M2, d, s, &h->launches));
-  RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s, Q_KV, k.qscratch));
-  KL(launch_layer_norm(k.cat, 2 * d, k.u, d, h->n2_g, h->n2_b, q.M, d, s, &h->launches));
-  RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s, Q_Q, k.qscratch));
+  if (h->w_kv_ln) {          // fp32 model: norm1 / norm2 folded into the k | v and q projections
+    RET(linear_ln(h, k, k.g2n, d, h->w_kv_ln, h->b_kv_ln, h->s_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, s));
+    RET(linear_ln(h, k, k.cat, 2 * d, h->w_q_ln, h->b_q_ln, h->s_q, k.qb, att, q.M, d, att, ACT_NONE, s));
+  } else {
+    KL(launch_layer_norm(k.g2n, d, k.g2n, d, h->n1_g, h->n1_b, q.M2, d, s, &h->launches));
+    RET(linear(h, k.g2n, d, h->w_kv, h->b_kv, k.kv, 2 * att, q.M2, d, 2 * att, ACT_NONE, 0, nullptr, 0, s, Q_KV, k.qscratch));
+    KL(launch_layer_norm(k.cat, 2 * d, k.u, d, h->n2_g, h->n2_b, q.M, d, s, &h->launches));
+    RET(linear(h, k.u, d, h->w_q, h->b_q, k.qb, att, q.M, d, att, ACT_NONE, 0, nullptr, 0, s, Q_Q, k.qscratch));
+  }
   KL(launch_attention(k.qb, att, k.kv, k.ob, att, q.B, q.L, q.K2, h->cfg.attention_heads,
                       att / h->cfg.attention_heads, s, &h->launches, k.rag));
   RET(linear(h, k.ob, att, h->w_o, h->b_o, k.cat + d, 2 * d, q.M, att, d, ACT_NONE, 0, nullptr, 0, s, Q_O, k.qscratch));
-  RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s, Q_F3, k.qscratch));
-  KL(launch_gate_mix(k.f3, k.fm, q.M, d, s, &h->launches));
+  if (h->w_f3p) {            // fp32 model: gate | local | global in one projection whose epilogue mixes them
+    GemmArgs g;
+    g.A = k.cat; g.lda = 2 * d; g.W = h->w_f3p; g.bias = h->b_f3p; g.C = k.fm; g.ldc = d;
+    g.M = q.M; g.N = 3 * d; g.K = 2 * d; g.gate = 1;
+    RET(gemm(h, g, s));
+  } else {
+    RET(linear(h, k.cat, 2 * d, h->w_f3, h->b_f3, k.f3, 3 * d, q.M, 2 * d, 3 * d, ACT_NONE, 0, nullptr, 0, s, Q_F3, k.qscratch));
+    KL(launch_gate_mix(k.f3, k.fm, q.M, d, s, &h->launches));
+  }
   RET(linear(h, k.fm, d, h->w_fo, h->b_fo, k.fused, d, q.M, d, d, ACT_NONE, 0, nullptr, 0, s, Q_FO, k.qscratch));
   return VASR_OK;
 }
 
+// logits == NULL (fp32 model only): greedy decode, the head leaves per-frame argmax partials in k.amax_* instead
 int run_ctc_head(vasr_handle* h, const Dims& q, const Work& k, const float* x, float* logits, cudaStream_t s) {
+  if (h->w_ctc_ln) {         // fp32 model: the head's LayerNorm folded into its projection
+    GemmArgs g;
+    g.A = x; g.lda = q.d; g.W = h->w_ctc_ln; g.bias = h->b_ctc_ln; g.C = logits; g.ldc = q.V;
+    g.M = q.M; g.N = q.V; g.K = q.d;
+    g.ln_s = h->s_ctc; g.ln_stats = k.lnstat;
+    if (!logits) { g.amax_val = k.amax_val; g.amax_idx = k.amax_idx; }
+    return gemm(h, g, s);
+  }
+  if (!logits) return fail(VASR_ERR_STATE, "the FakeQuantize model decodes from its logits");
   KL(launch_layer_norm(x, q.d, k.u, q.d, h->ctc_g, h->ctc_b, q.M, q.d, s, &h->launches));
   RET(linear(h, k.u, q.d, h->w_ctc, h->b_ctc, logits, q.V, q.M, q.d, q.V, ACT_NONE, 0, nullptr, 0, s, Q_CTC, k.qscratch));
   return VASR_OK;
@@ -890,6 +975,8 @@ int vasr_commit_weights(vasr_handle* h) {
   DeviceGuard dev_guard(h->device);
   CK(cudaDeviceSynchronize());
   free_weights(h);
+  h->w_q_ln = h->b_q_ln = h->s_q = h->w_kv_ln = h->b_kv_ln = h->s_kv = nullptr;
+  h->w_ctc_ln = h->b_ctc_ln = h->s_ctc = h->w_f3p = h->b_f3p = nullptr;
   const vasr_config& c = h->cfg;
   const int d = c.d_model, nm = c.mel_bins, att = c.attention_dim;
   // temporal binding: conv.weight (d, mel, 3) -> (d, 3*mel) with k index = tap*mel + channel
@@ -945,6 +1032,14 @@ int vasr_commit_weights(vasr_handle* h) {
   bkv.insert(bkv.end(), vb->begin(), vb->end());
   RET(upload(h, wkv.data(), wkv.size(), &h->w_kv));
   RET(upload(h, bkv.data(), bkv.size(), &h->b_kv));
+  if (!h->quant) {
+    const std::vector<float>*qw, *qb;
+    RET(need(h, gc + "cross_attention.q_proj.weight", (int64_t)att * d, &qw));
+    RET(need(h, gc + "cross_attention.q_proj.bias", att, &qb));
+    RET(upload_folded(h, *qw, att, d, qb->data(), gc + "norm2.weight", gc + "norm2.bias", &h->w_q_ln, &h->b_q_ln, &h->s_q));
+    RET(upload_folded(h, wkv, 2 * att, d, bkv.data(), gc + "norm1.weight", gc + "norm1.bias", &h->w_kv_ln, &h->b_kv_ln,
+                      &h->s_kv));
+  }
   RET(up_w(h, gc + "cross_attention.out_proj.weight", (int64_t)d * att, d, &h->w_o));
   RET(up(h, gc + "cross_attention.out_proj.bias", d, &h->b_o));
   // fusion: one (3d x 2d) projection of [local | ctx]: gate rows, then local_proj on the left
@@ -969,12 +1064,30 @@ int vasr_commit_weights(vasr_handle* h) {
   bf3.insert(bf3.end(), cb2->begin(), cb2->end());
   RET(upload(h, wf3.data(), wf3.size(), &h->w_f3));
   RET(upload(h, bf3.data(), bf3.size(), &h->b_f3));
+  h->w_f3p = h->b_f3p = nullptr;
+  if (!h->quant && d % 64 == 0) {
+    std::vector<float> wp(wf3.size()), bp(bf3.size());
+    for (int rp = 0; rp < 3 * d; ++rp) {
+      const int r = gate_perm_row(rp, d);
+      memcpy(&wp[(size_t)rp * 2 * d], &wf3[(size_t)r * 2 * d], (size_t)2 * d * sizeof(float));
+      bp[(size_t)rp] = bf3[(size_t)r];
+    }
+    RET(upload(h, wp.data(), wp.size(), &h->w_f3p));
+    RET(upload(h, bp.data(), bp.size(), &h->b_f3p));
+  }
   RET(up_w(h, gc + "fusion.out_proj.weight", (int64_t)d * d, d, &h->w_fo));
   RET(up(h, gc + "fusion.out_proj.bias", d, &h->b_fo));
   RET(up(h, "ctc_head.proj.0.weight", d, &h->ctc_g));
   RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
   RET(up_w(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, c.vocab_size, &h->w_ctc));
   RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
+  if (!h->quant) {
+    const std::vector<float>*hw, *hb;
+    RET(need(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &hw));
+    RET(need(h, "ctc_head.proj.2.bias", c.vocab_size, &hb));
+    RET(upload_folded(h, *hw, c.vocab_size, d, hb->data(), "ctc_head.proj.0.weight", "ctc_head.proj.0.bias", &h->w_ctc_ln,
+                      &h->b_ctc_ln, &h->s_ctc));
+  }
   h->quant_active = h->quant;
   if (h->quant_active) RET(setup_qsites(h));
   h->committed = true;
@@ -1190,7 +1303,8 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
   CallOrder call_order(h, s);
   const Dims q = make_dims(h, B, S, vasr_num_frames(S));
   Work k;
-  RET(ensure_workspace(h, q, true, true, &k, host));
+  const bool from_parts = h->w_ctc_ln != nullptr;       // fp32 model: the head's epilogue does the argmax, no logits
+  RET(ensure_workspace(h, q, true, !from_parts, &k, host));
   if (sample_lens) RET(upload_ragged(h, q, k, sample_lens, true, s));
   if (host) {
     tokens_dev = k.tok_stage;
@@ -1200,9 +1314,14 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
   if (host) RET(run_mel_from_host(h, q, k, pcm_host, s));
   else RET(run_mel(h, q, k, pcm_dev, 1, s));
   KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag));
-  RET(run_model(h, q, k, k.logits, nullptr, nullptr, nullptr, s));
-  KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));
-  KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches, k.rag));
+  RET(run_model(h, q, k, from_parts ? nullptr : k.logits, nullptr, nullptr, nullptr, s));
+  if (from_parts) {
+    KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches, k.rag, k.amax_val, k.amax_idx,
+                           argmax_slots(q.V)));
+  } else {
+    KL(launch_argmax(k.logits, k.pred, q.M, q.V, s, &h->launches));
+    KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches, k.rag));
+  }
   timing_end(h, s);
   if (host) {
     CK(cudaMemcpyAsync(tokens_host, tokens_dev, (size_t)q.M * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -222,7 +222,20 @@ struct TcArgs {
                       // are loaded once into the W halves of the stage ring (k-block kb always meets stage kb % nkb
                       // because nkb divides the ring) and only A streams afterwards
   long long* trace;   // debug: CTA 0 records clock64 at pipeline events (role, slot); NULL in production
+  // LayerNorm folded into the projection (EPI_LNA): the rows of A are the LayerNorm's INPUT, W carries gamma, the
+  // bias carries W beta; the converter thread that owns a row accumulates its sum and sum of squares while it
+  // converts the k-blocks and leaves (rstd, -mean * rstd) in ln_stats, the epilogue applies
+  // rstd * acc - mean * rstd * ln_s[n] + bias[n]  (ln_s[n] = sum_k W'[n, k]).
+  const float* ln_s;
+  float2* ln_stats;   // (M) scratch, one entry per row of A
+  float ln_eps;
+  // EPI_AMAX: per-row (max, argmax) over the columns each epilogue warp sees instead of the output itself:
+  // slot p = 2 * n_tile + half at amax_val / amax_idx[p * M + row]
+  float* amax_val;
+  int32_t* amax_idx;
 };
+// epilogue variants (template bit mask)
+constexpr int EPI_LNA = 1, EPI_AMAX = 2, EPI_GATE = 4;
 // tile -> (m tile, n tile).  A persistent CTA takes tiles blockIdx.x, + gridDim.x, ...; with an n-tile
 // count that divides the grid every tile of a CTA would have the same n index, and the CTAs that own
 // the narrow last n-tile would do half the work of the others.  The n index is therefore rotated by
@@ -252,7 +265,7 @@ __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
 // Epilogue of one warp over its tiles (shared by the single-CTA and the CTA-pair kernels).  PAIR: tiles are 256
 // rows shared by the two CTAs of a cluster (this CTA owns rows rank*128 ..), tile index strides over pairs, and
 // the accumulator-empty barrier lives in the leader CTA (arrive through its shared::cluster address).
-template <int ACT, bool PE, bool RESID, bool QUANT, bool PAIR>
+template <int ACT, bool PE, bool RESID, bool QUANT, bool PAIR, int EPI = 0>
 __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
                                               uint32_t tile_stride, uint32_t total_tiles32, uint32_t units, uint32_t rank,
                                               uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
@@ -304,14 +317,76 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
     const int64_t mrow0 = (int64_t)batch * rpb + mi0;               // global row of the warp's first row
     float* crow = g.C + mrow0 * g.ldc + n0;
     const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
-    float4 b4[2], qs4[2], qz4[2], pf4[2];
+    if constexpr ((EPI & EPI_AMAX) != 0) {
+      // Greedy decode never needs the logits: thread = row keeps its 64 columns in registers, applies bias (and
+      // the folded LayerNorm) per column and leaves (max, first index of the max) of what it saw; the collapse
+      // kernel takes the best of a row's partials in column order (ties -> lowest index, as torch.argmax).
+      static_assert(!PE && !RESID && !QUANT && ACT == ACT_NONE, "argmax epilogue: plain projection only");
+      const uint32_t r = mi0 + lane;
+      const int64_t grow = (int64_t)batch * rpb + r;
+      const int64_t slot = ((int64_t)nt * 2 + chalf) * g.M + grow;
+      mbar_wait(BARF(acc), (it >> 1) & 1u);
+      tc_fence_after();
+      if (c_begin >= c_end) {
+        tc_fence_before();
+        arrive_empty(acc);
+        if (r < rpb) { g.amax_val[slot] = -INFINITY; g.amax_idx[slot] = -1; }
+        continue;
+      }
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
+      tmem_ld32_issue(taddr, v0);
+      if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+      float rs = 1.f, ms = 0.f;
+      if ((EPI & EPI_LNA) && r < rpb) {
+        const float2 t = __ldcg(g.ln_stats + grow);
+        rs = t.x; ms = t.y;
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      arrive_empty(acc);
+      float best = -INFINITY;
+      int bi = -1;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (c_begin + j >= c_end) break;
+        const uint32_t nb = ncol0 + (c_begin + j) * 32;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const uint32_t n = nb + 4 * k4;
+          if (n >= (uint32_t)g.N) break;                               // N % 4 == 0: the group is valid as a whole
+          const float4 b = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 t = b;
+          if (EPI & EPI_LNA) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.ln_s + n));
+            t.x = fmaf(ms, sc.x, b.x); t.y = fmaf(ms, sc.y, b.y); t.z = fmaf(ms, sc.z, b.z); t.w = fmaf(ms, sc.w, b.w);
+          }
+          const float a0 = __uint_as_float(j == 0 ? v0[4 * k4] : v1[4 * k4]);
+          const float a1 = __uint_as_float(j == 0 ? v0[4 * k4 + 1] : v1[4 * k4 + 1]);
+          const float a2 = __uint_as_float(j == 0 ? v0[4 * k4 + 2] : v1[4 * k4 + 2]);
+          const float a3 = __uint_as_float(j == 0 ? v0[4 * k4 + 3] : v1[4 * k4 + 3]);
+          const float x0 = (EPI & EPI_LNA) ? fmaf(rs, a0, t.x) : a0 + t.x;
+          const float x1 = (EPI & EPI_LNA) ? fmaf(rs, a1, t.y) : a1 + t.y;
+          const float x2 = (EPI & EPI_LNA) ? fmaf(rs, a2, t.z) : a2 + t.z;
+          const float x3 = (EPI & EPI_LNA) ? fmaf(rs, a3, t.w) : a3 + t.w;
+          if (x0 > best || bi < 0) { best = x0; bi = (int)n; }
+          if (x1 > best) { best = x1; bi = (int)n + 1; }
+          if (x2 > best) { best = x2; bi = (int)n + 2; }
+          if (x3 > best) { best = x3; bi = (int)n + 3; }
+        }
+      }
+      if (r < rpb) { g.amax_val[slot] = best; g.amax_idx[slot] = bi; }
+      continue;
+    }
+    float4 b4[2], qs4[2], qz4[2], pf4[2], s4[2];
     bool col_ok[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t n = n0 + 32 * j;
       col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;       // N % 4 == 0: the group is valid as a whole
-      b4[j] = qs4[j] = qz4[j] = pf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b4[j] = qs4[j] = qz4[j] = pf4[j] = s4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if ((EPI & EPI_LNA) && col_ok[j]) s4[j] = __ldg(reinterpret_cast<const float4*>(g.ln_s + n));
       if (QUANT && col_ok[j]) {
         qs4[j] = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
         qz4[j] = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
@@ -341,9 +416,17 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
     }
     uint32_t v0[32], v1[32];
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
+    float2 st[8];
     if (!(g.dbg & 1)) {
       tmem_ld32_issue(taddr, v0);
       if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+      if constexpr ((EPI & EPI_LNA) != 0) {      // row statistics the converters of this tile left (behind the TMEM loads)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = 4 * i + rsub;
+          st[i] = mi0 + rr < rpb ? __ldcg(g.ln_stats + mrow0 + rr) : make_float2(1.f, 0.f);
+        }
+      }
       tmem_ld_wait();
     } else {
 #pragma unroll
@@ -372,7 +455,12 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
       for (int i = 0; i < 8; ++i) {
         const uint32_t rr = 4 * i + rsub;
         float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        if constexpr ((EPI & EPI_LNA) != 0) {
+          x.x = fmaf(st[i].x, x.x, fmaf(st[i].y, s4[j].x, b4[j].x)); x.y = fmaf(st[i].x, x.y, fmaf(st[i].y, s4[j].y, b4[j].y));
+          x.z = fmaf(st[i].x, x.z, fmaf(st[i].y, s4[j].z, b4[j].z)); x.w = fmaf(st[i].x, x.w, fmaf(st[i].y, s4[j].w, b4[j].w));
+        } else {
+          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        }
         if (QUANT) {
           x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
           x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
@@ -406,7 +494,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 // three per warp.  Two chunks are read at once as above; the first is transposed and stored, then its registers
 // take the third chunk and only then is the accumulator handed back (the tile's MMAs take 13.8 k clocks, the
 // epilogue has time).  Same staging, same coalesced 128-byte row segments as epilogue_loop.
-template <int ACT, bool RESID>
+template <int ACT, bool RESID, int EPI = 0>
 __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
                                                  uint32_t tile_stride, uint32_t total_tiles32, uint32_t rank,
                                                  uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
@@ -440,14 +528,76 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
     const int64_t mrow0 = (int64_t)batch * rpb + mi0;
     float* crow = g.C + mrow0 * g.ldc + n0;
     const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
-    float4 b4[3];
+    float4 b4[3], s4[3];
     bool col_ok[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const uint32_t n = n0 + 32 * j;
       col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;
-      b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b4[j] = s4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if ((EPI & EPI_LNA) && col_ok[j]) s4[j] = __ldg(reinterpret_cast<const float4*>(g.ln_s + n));
+    }
+    if constexpr ((EPI & EPI_GATE) != 0) {
+      // GatedFusion (attention.py:191-220): the weight rows were permuted at pack time so that the three chunks of
+      // this warp are gate logits | local_proj | global_proj of the SAME 32 channels (64 * nt + 32 * chalf ..); the
+      // mix s * l + (1 - s) * t happens here and only the 192 mixed channels are written (C is M x N/3).
+      static_assert(!RESID && ACT == ACT_NONE && !(EPI & EPI_LNA), "gate epilogue: plain stacked projection");
+      float* orow = g.C + mrow0 * g.ldc + nt * 64 + chalf * 32 + 4 * cc;
+      mbar_wait(bar_tfull0 + 8u * acc, (it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c_begin * 32;
+      tmem_ld32_issue(taddr, v0);
+      tmem_ld32_issue(taddr + 32, v1);
+      tmem_ld_wait();
+      float4 gx[8], lx[8];
+      auto take = [&](const uint32_t (&v)[32], int j, float4 (&o)[8]) {
+        uint8_t* srow = stg + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = 4 * i + rsub;
+          float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+          o[i] = x;
+        }
+        __syncwarp();
+      };
+      take(v0, 0, gx);
+      tmem_ld32_issue(taddr + 64, v0);
+      tmem_ld_wait();
+      tc_fence_before();
+      arrive_empty(acc);
+      take(v1, 1, lx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gx[i].x = sigmoid_f(gx[i].x); gx[i].y = sigmoid_f(gx[i].y); gx[i].z = sigmoid_f(gx[i].z); gx[i].w = sigmoid_f(gx[i].w);
+      }
+      {
+        uint8_t* srow = stg + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(srow + ((k ^ (lane & 7)) << 4)) = make_uint4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = 4 * i + rsub;
+          float4 t = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          t.x += b4[2].x; t.y += b4[2].y; t.z += b4[2].z; t.w += b4[2].w;
+          float4 o;
+          o.x = gx[i].x * lx[i].x + (1.0f - gx[i].x) * t.x;
+          o.y = gx[i].y * lx[i].y + (1.0f - gx[i].y) * t.y;
+          o.z = gx[i].z * lx[i].z + (1.0f - gx[i].z) * t.z;
+          o.w = gx[i].w * lx[i].w + (1.0f - gx[i].w) * t.w;
+          if (mi0 + rr < rpb) *reinterpret_cast<float4*>(orow + (int64_t)rr * g.ldc) = o;
+        }
+        __syncwarp();
+      }
+      continue;
     }
     float4 r4[8];
     auto load_resid = [&](int j) {
@@ -471,6 +621,14 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c_begin * 32;
     tmem_ld32_issue(taddr, v0);
     if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
+    float2 st[8];
+    if constexpr ((EPI & EPI_LNA) != 0) {        // row statistics the converters of this tile left (behind the TMEM loads)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t rr = 4 * i + rsub;
+        st[i] = mi0 + rr < rpb ? __ldcg(g.ln_stats + mrow0 + rr) : make_float2(1.f, 0.f);
+      }
+    }
     tmem_ld_wait();
     // chunk j of this warp: registers -> swizzled staging -> 128-byte row segments (+ bias, residual) -> global
     auto emit = [&](const uint32_t (&v)[32], int j) {
@@ -483,7 +641,12 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
       for (int i = 0; i < 8; ++i) {
         const uint32_t rr = 4 * i + rsub;
         float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        if constexpr ((EPI & EPI_LNA) != 0) {
+          x.x = fmaf(st[i].x, x.x, fmaf(st[i].y, s4[j].x, b4[j].x)); x.y = fmaf(st[i].x, x.y, fmaf(st[i].y, s4[j].y, b4[j].y));
+          x.z = fmaf(st[i].x, x.z, fmaf(st[i].y, s4[j].z, b4[j].z)); x.w = fmaf(st[i].x, x.w, fmaf(st[i].y, s4[j].w, b4[j].w));
+        } else {
+          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+        }
         if (ACT != ACT_NONE && n0 + 32 * j >= (uint32_t)g.act_from) {
           if (ACT == ACT_GELU) {
             gelu_poly2(x.x, x.y);
@@ -806,7 +969,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false, int TN = 128>
+template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false, int TN = 128, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                 const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
@@ -979,6 +1142,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t stage = 0, phase = 0, cnt = 0;
     int tr_i = 0;
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+      // EPI_LNA: this thread sees its whole row of A go by; sum and sum of squares on the packed pipe
+      u64 sum2[2] = {0ull, 0ull}, sq2[2] = {0ull, 0ull}, shift2 = 0ull;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(PB_AFULL + stage), phase);
         if (threadIdx.x == 64) trace_ev(g, 1, tr_i);
@@ -991,6 +1156,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           hi[4 * c + 1] = rna_tf32(v.y); lo[4 * c + 1] = rna_tf32(v.y - __uint_as_float(hi[4 * c + 1]));
           hi[4 * c + 2] = rna_tf32(v.z); lo[4 * c + 2] = rna_tf32(v.z - __uint_as_float(hi[4 * c + 2]));
           hi[4 * c + 3] = rna_tf32(v.w); lo[4 * c + 3] = rna_tf32(v.w - __uint_as_float(hi[4 * c + 3]));
+          if constexpr ((EPI & EPI_LNA) != 0) {
+            // shifted by the row's first element, so that a common offset of the row does not cancel in
+            // E[x^2] - mean^2
+            if (kb == 0 && c == 0) shift2 = pack2(-v.x, -v.x);
+            const u64 a = add2(pack2(v.x, v.y), shift2), b = add2(pack2(v.z, v.w), shift2);
+            sum2[0] = add2(sum2[0], a); sum2[1] = add2(sum2[1], b);
+            sq2[0] = fma2(a, a, sq2[0]); sq2[1] = fma2(b, b, sq2[1]);
+          }
+        }
+        if constexpr ((EPI & EPI_LNA) != 0) {
+          if (kb == nkb - 1) {
+            // columns past K arrive as zeros (TMA fill) and add nothing.  The entry is written before this
+            // warp's arrive on the conversion barrier of the tile's last k-block, which the tile's last MMAs,
+            // their commit and the epilogue's wait for the accumulator all follow.
+            int nt_unused;
+            int64_t mt;
+            tile_coords(g, tile, UNITS, &mt, &nt_unused);
+            const uint32_t r = ((uint32_t)mt % (uint32_t)g.m_tiles_per_batch) * 2u * TBM + rank * TBM + (uint32_t)row;
+            if (r < (uint32_t)g.rows_per_batch) {
+              const float inv = 1.0f / (float)g.K;
+              const float dm = (hsum2(sum2[0]) + hsum2(sum2[1])) * inv;             // mean of the shifted row
+              const float var = fmaxf(fmaf(-dm, dm, (hsum2(sq2[0]) + hsum2(sq2[1])) * inv), 0.f);
+              float sh, sh_unused;
+              unpack2(shift2, sh, sh_unused);
+              const float mean = dm - sh;
+              const float rstd = 1.0f / sqrtf(var + g.ln_eps);
+              g.ln_stats[(int64_t)((uint32_t)mt / (uint32_t)g.m_tiles_per_batch) * g.rows_per_batch + r] =
+                  make_float2(rstd, -mean * rstd);
+            }
+          }
         }
         // the TMEM slot is free once the MMAs of its previous use (P_ASLOTS k-steps ago) have completed
         const uint32_t slot = cnt % P_ASLOTS;
@@ -1012,11 +1207,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
     if constexpr (TN == 192) {
       static_assert(TN != 192 || (ACT != ACT_SIGMOID && !PE && !QUANT), "192-column tiles: no pos-enc / quantised / sigmoid epilogue");
-      epilogue_loop192<ACT, RESID>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+      epilogue_loop192<ACT, RESID, EPI>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
                               (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, rank, BAR(PB_TFULL),
                               BAR(PB_TEMPTY));
     } else {
-      epilogue_loop<ACT, PE, RESID, QUANT, true>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+      static_assert(!(EPI & EPI_GATE), "the gate epilogue exists for 192-column tiles only");
+      epilogue_loop<ACT, PE, RESID, QUANT, true, EPI>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
                                                  (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
                                                  BAR(PB_TFULL), BAR(PB_TEMPTY));
     }
@@ -1122,10 +1318,20 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   // converted.  Measured against the 128-column tiling (W resident where it applied): in_proj -9 %, x / dt -6 %,
   // out_proj / ffn2 -18 %, fusion -17 %.  Instantiated for the plain (+ residual), softplus and GELU epilogues.
   // VASR_TC_T192=2 restricts it to the N that would otherwise end in a 64-column tile.
-  const bool inst192 = !g.pe_time && !g.q_scale && (g.act == ACT_NONE || ((g.act == ACT_SOFTPLUS || g.act == ACT_GELU) && !g.resid));
+  // epilogue variants: folded LayerNorm (ln_s), argmax partials instead of the output (amax_val), gated fusion
+  const bool lna = g.ln_s != nullptr, amax = g.amax_val != nullptr, gate = g.gate != 0;
+  if (lna && (!pair || !g.ln_stats || g.K % TBK != 0 || g.K / TBK <= 4 || g.pe_time || g.resid || g.q_scale ||
+              !(reinterpret_cast<uintptr_t>(g.ln_s) % 16 == 0) || !(g.act == ACT_NONE || (g.act == ACT_GELU && !amax))))
+    return cudaErrorNotSupported;      // K / 32 > A slots: a row's entry is not rewritten before its tile's epilogue read it
+  if (amax && (!pair || !g.amax_idx || g.act != ACT_NONE || g.pe_time || g.resid || g.q_scale || gate)) return cudaErrorNotSupported;
+  if (gate && (!pair || lna || g.act != ACT_NONE || g.pe_time || g.resid || g.q_scale || g.N % 192 != 0)) return cudaErrorNotSupported;
+  const bool inst192 = !g.pe_time && !g.q_scale && !amax && (!lna || g.act == ACT_GELU) &&
+                       (g.act == ACT_NONE || ((g.act == ACT_SOFTPLUS || g.act == ACT_GELU) && !g.resid));
   const int64_t r192 = g.N % 192;
   bool t192 = pair && t192_env && inst192 && (r192 == 0 || r192 >= TBN);
   if (t192_env == 2 && g.N % TBN == 0) t192 = false;
+  if (gate && !t192) return cudaErrorNotSupported;
+  if (lna && g.act == ACT_GELU && !t192) return cudaErrorNotSupported;   // instantiated for the 192-column tiles only
   const int tn = t192 ? 192 : TBN;
   CUtensorMap tmA, tmWh, tmWl;
   {
@@ -1151,6 +1357,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   a.q_scale = g.q_scale; a.q_zp = g.q_zp;
   a.resid = g.resid; a.ldr = g.ldr;
   a.pe_time = g.pe_time; a.pe_freq = g.pe_freq; a.pe_half = g.pe_half;
+  a.ln_s = g.ln_s; a.ln_stats = reinterpret_cast<float2*>(g.ln_stats); a.ln_eps = g.ln_eps;
+  a.amax_val = g.amax_val; a.amax_idx = g.amax_idx;
   a.trace = g_trace;
   static const int rot_env = debug_env_int("VASR_TC_ROT", 1);
   a.rotate_n = rot_env;
@@ -1193,10 +1401,26 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t s, int64
   };
   if (t192) {
     a.rotate_n = 0;
-    if (g.act == ACT_SOFTPLUS) go192(gemm_tc2_kernel<ACT_SOFTPLUS, false, false, false, false, 192>);
+    if (gate) go192(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 192, EPI_GATE>);
+    else if (lna) go192(gemm_tc2_kernel<ACT_GELU, false, false, false, false, 192, EPI_LNA>);
+    else if (g.act == ACT_SOFTPLUS) go192(gemm_tc2_kernel<ACT_SOFTPLUS, false, false, false, false, 192>);
     else if (g.act == ACT_GELU) go192(gemm_tc2_kernel<ACT_GELU, false, false, false, false, 192>);
     else if (rs) go192(gemm_tc2_kernel<ACT_NONE, false, true, false, false, 192>);
     else go192(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 192>);
+    if (err != cudaSuccess) return err;
+    if (launches) ++*launches;
+    return cudaSuccess;
+  }
+  if (lna || amax) {      // plain projection with a folded LayerNorm and / or the argmax epilogue (CTC head, q, k | v)
+    if (a.wres) {
+      if (lna && amax) go2(gemm_tc2_kernel<ACT_NONE, false, false, false, true, 128, EPI_LNA | EPI_AMAX>);
+      else if (lna) go2(gemm_tc2_kernel<ACT_NONE, false, false, false, true, 128, EPI_LNA>);
+      else go2(gemm_tc2_kernel<ACT_NONE, false, false, false, true, 128, EPI_AMAX>);
+    } else {
+      if (lna && amax) go2(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 128, EPI_LNA | EPI_AMAX>);
+      else if (lna) go2(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 128, EPI_LNA>);
+      else go2(gemm_tc2_kernel<ACT_NONE, false, false, false, false, 128, EPI_AMAX>);
+    }
     if (err != cudaSuccess) return err;
     if (launches) ++*launches;
     return cudaSuccess;

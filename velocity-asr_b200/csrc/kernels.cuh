@@ -30,6 +30,17 @@ struct GemmArgs {
   int act_from = 0;
   const float* resid = nullptr;
   int64_t ldr = 0;
+  // LayerNorm folded into the projection (tensor-core kernel): A holds the LayerNorm's INPUT rows (K = the
+  // normalised width), W is W diag(gamma), bias is b + W beta, ln_s[n] = sum_k W'[n, k]; ln_stats: (M, 2) scratch
+  const float* ln_s = nullptr;
+  float* ln_stats = nullptr;
+  float ln_eps = 1e-5f;
+  // greedy decode: instead of C, per row and slot p = 2 * (n / 128) + half the (max, first argmax) of the columns
+  // the slot covers, at amax_val / amax_idx[p * M + m]; launch_ctc_collapse takes them (argmax_slots(N) slots)
+  float* amax_val = nullptr;
+  int32_t* amax_idx = nullptr;
+  // GatedFusion: W rows permuted by gate_perm_row (N = 3 C): C[m, c] = s l + (1 - s) t, s = sigmoid(gate), C is (M, C)
+  int gate = 0;
   const float* pe_time = nullptr;  // (>= pe_rows, pe_half)
   const float* pe_freq = nullptr;  // (N - pe_half)
   int pe_half = 0;
@@ -127,9 +138,13 @@ cudaError_t launch_argmax(const float* logits, int32_t* pred, int64_t M, int V, 
 // tokens / starts / ends (B, L) left-packed: run starts of equal non-blank predictions, with [start, end) frames
 cudaError_t launch_ctc_runs(const int32_t* pred, int32_t* tokens, int32_t* starts, int32_t* ends, int32_t* lens,
                             int64_t B, int64_t L, int blank, cudaStream_t s, int64_t* launches);
-cudaError_t launch_ctc_collapse(const int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
+// amax_val / amax_idx (slots x B*L): each frame's prediction is first taken from the CTC-head projection's argmax
+// partials (GemmArgs::amax_val) and written to `pred`
+inline int argmax_slots(int64_t N) { return (int)(2 * ((N + 127) / 128)); }
+cudaError_t launch_ctc_collapse(int32_t* pred, int32_t* tokens, int32_t* lens, int64_t B, int64_t L,
                                 int blank, int collapse, cudaStream_t s, int64_t* launches,
-                                const int32_t* rag = nullptr);
+                                const int32_t* rag = nullptr, const float* amax_val = nullptr,
+                                const int32_t* amax_idx = nullptr, int slots = 0);
 
 // ---------------------------------------------------------------- CTC prefix beam search
 // per (utterance, frame) row: stats = (max, log sum exp(x - max)); top_tok (M, K) = the K best non-blank
