@@ -268,7 +268,8 @@ __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
 template <int ACT, bool PE, bool RESID, bool QUANT, bool PAIR, int EPI = 0>
 __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
                                               uint32_t tile_stride, uint32_t total_tiles32, uint32_t units, uint32_t rank,
-                                              uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
+                                              uint32_t bar_tfull0, uint32_t bar_tempty0_local,
+                                              const float2* sstats = nullptr) {
   constexpr uint32_t tmem_base = 0u;
   constexpr uint32_t TM = PAIR ? 2 * TBM : TBM;          // rows of one tile
   auto BARF = [&](uint32_t acc) { return bar_tfull0 + 8u * acc; };
@@ -338,8 +339,8 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
       tmem_ld32_issue(taddr, v0);
       if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
       float rs = 1.f, ms = 0.f;
-      if ((EPI & EPI_LNA) && r < rpb) {
-        const float2 t = __ldcg(g.ln_stats + grow);
+      if (EPI & EPI_LNA) {       // left by this tile's converters in shared memory (the staging area is unused here)
+        const float2 t = sstats[(it & 1u) * TBM + q * 32 + lane];
         rs = t.x; ms = t.y;
       }
       tmem_ld_wait();
@@ -378,15 +379,14 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
       if (r < rpb) { g.amax_val[slot] = best; g.amax_idx[slot] = bi; }
       continue;
     }
-    float4 b4[2], qs4[2], qz4[2], pf4[2], s4[2];
+    float4 b4[2], qs4[2], qz4[2], pf4[2];
     bool col_ok[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t n = n0 + 32 * j;
       col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;       // N % 4 == 0: the group is valid as a whole
-      b4[j] = qs4[j] = qz4[j] = pf4[j] = s4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-      if ((EPI & EPI_LNA) && col_ok[j]) s4[j] = __ldg(reinterpret_cast<const float4*>(g.ln_s + n));
+      b4[j] = qs4[j] = qz4[j] = pf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(EPI & EPI_LNA) && col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
       if (QUANT && col_ok[j]) {
         qs4[j] = __ldg(reinterpret_cast<const float4*>(g.q_scale + n));
         qz4[j] = __ldg(reinterpret_cast<const float4*>(g.q_zp + n));
@@ -416,18 +416,38 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
     }
     uint32_t v0[32], v1[32];
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + c_begin * 32;
-    float2 st[8];
     if (!(g.dbg & 1)) {
       tmem_ld32_issue(taddr, v0);
       if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
-      if constexpr ((EPI & EPI_LNA) != 0) {      // row statistics the converters of this tile left (behind the TMEM loads)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t rr = 4 * i + rsub;
-          st[i] = mi0 + rr < rpb ? __ldcg(g.ln_stats + mrow0 + rr) : make_float2(1.f, 0.f);
-        }
+      float2 own = make_float2(1.f, 0.f);
+      if constexpr ((EPI & EPI_LNA) != 0) {
+        if (mi0 + lane < rpb) own = __ldcg(g.ln_stats + mrow0 + lane);   // left by this tile's converters
       }
       tmem_ld_wait();
+      if constexpr ((EPI & EPI_LNA) != 0) {
+        // thread = row:  rstd * acc + (-mean * rstd * s[n] + bias[n])  on the chunks as they sit in registers
+        const u64 rs2 = pack2(own.x, own.x), ms2 = pack2(own.y, own.y);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (c_begin + j >= c_end) break;
+          const uint32_t nb = ncol0 + (c_begin + j) * 32;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            if (nb + 4 * k4 >= (uint32_t)g.N) break;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.ln_s + nb + 4 * k4));
+            const float4 bc = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + nb + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t* v = j == 0 ? v0 : v1;
+            u64 a = pack2(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]));
+            u64 b = pack2(__uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
+            a = fma2(rs2, a, fma2(ms2, pack2(sc.x, sc.y), pack2(bc.x, bc.y)));
+            b = fma2(rs2, b, fma2(ms2, pack2(sc.z, sc.w), pack2(bc.z, bc.w)));
+            float f0, f1, f2, f3;
+            unpack2(a, f0, f1); unpack2(b, f2, f3);
+            v[4 * k4] = __float_as_uint(f0); v[4 * k4 + 1] = __float_as_uint(f1);
+            v[4 * k4 + 2] = __float_as_uint(f2); v[4 * k4 + 3] = __float_as_uint(f3);
+          }
+        }
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 32; ++k) v0[k] = v1[k] = 0u;
@@ -455,12 +475,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
       for (int i = 0; i < 8; ++i) {
         const uint32_t rr = 4 * i + rsub;
         float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        if constexpr ((EPI & EPI_LNA) != 0) {
-          x.x = fmaf(st[i].x, x.x, fmaf(st[i].y, s4[j].x, b4[j].x)); x.y = fmaf(st[i].x, x.y, fmaf(st[i].y, s4[j].y, b4[j].y));
-          x.z = fmaf(st[i].x, x.z, fmaf(st[i].y, s4[j].z, b4[j].z)); x.w = fmaf(st[i].x, x.w, fmaf(st[i].y, s4[j].w, b4[j].w));
-        } else {
-          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
-        }
+        if constexpr ((EPI & EPI_LNA) == 0) { x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w; }
         if (QUANT) {
           x.x = fake_quant_u8(x.x, qs4[j].x, qz4[j].x); x.y = fake_quant_u8(x.y, qs4[j].y, qz4[j].y);
           x.z = fake_quant_u8(x.z, qs4[j].z, qz4[j].z); x.w = fake_quant_u8(x.w, qs4[j].w, qz4[j].w);
@@ -495,7 +510,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
 // take the third chunk and only then is the accumulator handed back (the tile's MMAs take 13.8 k clocks, the
 // epilogue has time).  Same staging, same coalesced 128-byte row segments as epilogue_loop.
 template <int ACT, bool RESID, int EPI = 0>
-__device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, int warp, int lane, uint32_t first_tile,
+__device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, float2* rowfac, const float2* sstats, int warp, int lane, uint32_t first_tile,
                                                  uint32_t tile_stride, uint32_t total_tiles32, uint32_t rank,
                                                  uint32_t bar_tfull0, uint32_t bar_tempty0_local) {
   constexpr uint32_t tmem_base = 0u;
@@ -528,15 +543,14 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
     const int64_t mrow0 = (int64_t)batch * rpb + mi0;
     float* crow = g.C + mrow0 * g.ldc + n0;
     const float* rrow = RESID ? g.resid + mrow0 * g.ldr + n0 : nullptr;
-    float4 b4[3], s4[3];
+    float4 b4[3];
     bool col_ok[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const uint32_t n = n0 + 32 * j;
       col_ok[j] = (c_begin + j < c_end) && n < (uint32_t)g.N;
-      b4[j] = s4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col_ok[j] && g.bias) b4[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-      if ((EPI & EPI_LNA) && col_ok[j]) s4[j] = __ldg(reinterpret_cast<const float4*>(g.ln_s + n));
     }
     if constexpr ((EPI & EPI_GATE) != 0) {
       // GatedFusion (attention.py:191-220): the weight rows were permuted at pack time so that the three chunks of
@@ -621,13 +635,18 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c_begin * 32;
     tmem_ld32_issue(taddr, v0);
     if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
-    float2 st[8];
-    if constexpr ((EPI & EPI_LNA) != 0) {        // row statistics the converters of this tile left (behind the TMEM loads)
+    // EPI_LNA: the thread that owns a row of the accumulator fetches the row's (rstd, -mean * rstd) and leaves
+    // them in this warp's row-factor table; after the transpose a lane picks up the factors of each of its rows
+    // next to the row segment itself (no long-lived registers, no per-column loads: the GELU epilogue is the
+    // critical path of ffn.0, every instruction here is paid in full)
+    float4 s4[3];
+    if constexpr ((EPI & EPI_LNA) != 0) {
+      // the converters' table is double-buffered by tile parity; it is copied before the accumulator is handed
+      // back, so the converters of tile it + 2 (which need that hand-over) cannot overwrite what is still in use
+      rowfac[lane] = sstats[(it & 1u) * TBM + q * 32 + lane];          // ordered by the __syncwarp of the first transpose
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t rr = 4 * i + rsub;
-        st[i] = mi0 + rr < rpb ? __ldcg(g.ln_stats + mrow0 + rr) : make_float2(1.f, 0.f);
-      }
+      for (int j = 0; j < 3; ++j)
+        s4[j] = col_ok[j] ? __ldg(reinterpret_cast<const float4*>(g.ln_s + n0 + 32 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tmem_ld_wait();
     // chunk j of this warp: registers -> swizzled staging -> 128-byte row segments (+ bias, residual) -> global
@@ -642,10 +661,18 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
         const uint32_t rr = 4 * i + rsub;
         float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cc ^ (rr & 7)) << 4));
         if constexpr ((EPI & EPI_LNA) != 0) {
-          x.x = fmaf(st[i].x, x.x, fmaf(st[i].y, s4[j].x, b4[j].x)); x.y = fmaf(st[i].x, x.y, fmaf(st[i].y, s4[j].y, b4[j].y));
-          x.z = fmaf(st[i].x, x.z, fmaf(st[i].y, s4[j].z, b4[j].z)); x.w = fmaf(st[i].x, x.w, fmaf(st[i].y, s4[j].w, b4[j].w));
+          // packed: a 3-register scalar FFMA occupies the FMA pipe as long as an FFMA2 does, and that pipe is what
+          // the GELU epilogue is bound by
+          const float2 f = rowfac[rr];
+          const u64 rs2 = pack2(f.x, f.x), ms2 = pack2(f.y, f.y);
+          const u64 lo = fma2(rs2, pack2(x.x, x.y), fma2(ms2, pack2(s4[j].x, s4[j].y), pack2(b4[j].x, b4[j].y)));
+          const u64 hi = fma2(rs2, pack2(x.z, x.w), fma2(ms2, pack2(s4[j].z, s4[j].w), pack2(b4[j].z, b4[j].w)));
+          unpack2(lo, x.x, x.y);
+          unpack2(hi, x.z, x.w);
         } else {
-          x.x += b4[j].x; x.y += b4[j].y; x.z += b4[j].z; x.w += b4[j].w;
+          const u64 lo = add2(pack2(x.x, x.y), pack2(b4[j].x, b4[j].y)), hi = add2(pack2(x.z, x.w), pack2(b4[j].z, b4[j].w));
+          unpack2(lo, x.x, x.y);
+          unpack2(hi, x.z, x.w);
         }
         if (ACT != ACT_NONE && n0 + 32 * j >= (uint32_t)g.act_from) {
           if (ACT == ACT_GELU) {
@@ -900,7 +927,8 @@ struct PairCfg {
   static constexpr int ASLOTS = TN == 128 ? 4 : 2;
   static constexpr uint32_t A0 = 2 * TN;                               // first A column (two accumulators before it)
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 512 + 1024;
+  static constexpr int ROWFAC_OFFSET = BAR_OFFSET + 512;                // TN = 192: 32 x float2 per epilogue warp (EPI_LNA)
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 512 + (TN == 192 ? EPI_WARPS * 256 + 2 * TBM * 8 : 0) + 1024;
   static constexpr int AFULL = 0, WFULL = STAGES, CONV = 2 * STAGES, EMPTY = 3 * STAGES, TFULL = 4 * STAGES,
                        TEMPTY = 4 * STAGES + 2, AFREE = 4 * STAGES + 4, NBARS = 4 * STAGES + 4 + ASLOTS;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
@@ -970,7 +998,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 
 template <int ACT, bool PE, bool RESID, bool QUANT, bool WRES = false, int TN = 128, int EPI = 0>
+#ifdef VASR_TC_MAXNREG
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(144)
+#else
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+#endif
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWh,
                 const __grid_constant__ CUtensorMap tmWl, const TcArgs g) {
   // the tile-width dependent layout, under the names the body uses (they shadow the TN = 128 globals)
@@ -983,6 +1015,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t TMEM_A0 = Cfg::A0;
   constexpr int W_HALF_BYTES = Cfg::W_HALF_BYTES;
   static_assert(!(WRES && TN != 128), "the W-resident schedule exists for 128-column tiles only");
+  // EPI_LNA: where the converters leave a tile's row statistics for its epilogue.  Shared memory (2 x 128 float2,
+  // by tile parity) where there is room — the 192-column layout, and the argmax epilogue, whose transpose staging
+  // is unused; global scratch otherwise (the epilogue then pays an L2 round trip per tile after the accumulator
+  // arrives: ~7 us on ffn.0 when it still took that route).
+  constexpr bool SSTATS = (EPI & EPI_LNA) != 0 && (TN == 192 || (EPI & EPI_AMAX) != 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
@@ -999,6 +1036,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const uint32_t stage0 = smem_u32(smem);
+  float2* sstats = reinterpret_cast<float2*>(TN == 192 ? smem + Cfg::ROWFAC_OFFSET + EPI_WARPS * 256
+                                                       : smem + P_STAGES * P_STAGE_BYTES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -1139,11 +1178,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + TMEM_A0;
-    uint32_t stage = 0, phase = 0, cnt = 0;
+    uint32_t stage = 0, phase = 0, cnt = 0, cit = 0;
     int tr_i = 0;
-    for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+    for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride, ++cit) {
       // EPI_LNA: this thread sees its whole row of A go by; sum and sum of squares on the packed pipe
-      u64 sum2[2] = {0ull, 0ull}, sq2[2] = {0ull, 0ull}, shift2 = 0ull;
+      u64 sum2[2] = {0ull, 0ull}, sq2[2] = {0ull, 0ull};
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(BAR(PB_AFULL + stage), phase);
         if (threadIdx.x == 64) trace_ev(g, 1, tr_i);
@@ -1157,10 +1196,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           hi[4 * c + 2] = rna_tf32(v.z); lo[4 * c + 2] = rna_tf32(v.z - __uint_as_float(hi[4 * c + 2]));
           hi[4 * c + 3] = rna_tf32(v.w); lo[4 * c + 3] = rna_tf32(v.w - __uint_as_float(hi[4 * c + 3]));
           if constexpr ((EPI & EPI_LNA) != 0) {
-            // shifted by the row's first element, so that a common offset of the row does not cancel in
-            // E[x^2] - mean^2
-            if (kb == 0 && c == 0) shift2 = pack2(-v.x, -v.x);
-            const u64 a = add2(pack2(v.x, v.y), shift2), b = add2(pack2(v.z, v.w), shift2);
+            const u64 a = pack2(v.x, v.y), b = pack2(v.z, v.w);
             sum2[0] = add2(sum2[0], a); sum2[1] = add2(sum2[1], b);
             sq2[0] = fma2(a, a, sq2[0]); sq2[1] = fma2(b, b, sq2[1]);
           }
@@ -1170,20 +1206,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // columns past K arrive as zeros (TMA fill) and add nothing.  The entry is written before this
             // warp's arrive on the conversion barrier of the tile's last k-block, which the tile's last MMAs,
             // their commit and the epilogue's wait for the accumulator all follow.
+            const float inv = 1.0f / (float)g.K;
+            if constexpr (SSTATS) {
+              // rows past the end of A arrive as zeros: finite statistics that nobody uses
+              const float mean = (hsum2(sum2[0]) + hsum2(sum2[1])) * inv;
+              const float var = fmaxf(fmaf(-mean, mean, (hsum2(sq2[0]) + hsum2(sq2[1])) * inv), 0.f);
+              const float rstd = 1.0f / sqrtf(var + g.ln_eps);
+              sstats[(cit & 1u) * TBM + row] = make_float2(rstd, -mean * rstd);
+            } else {
             int nt_unused;
             int64_t mt;
             tile_coords(g, tile, UNITS, &mt, &nt_unused);
             const uint32_t r = ((uint32_t)mt % (uint32_t)g.m_tiles_per_batch) * 2u * TBM + rank * TBM + (uint32_t)row;
             if (r < (uint32_t)g.rows_per_batch) {
-              const float inv = 1.0f / (float)g.K;
-              const float dm = (hsum2(sum2[0]) + hsum2(sum2[1])) * inv;             // mean of the shifted row
-              const float var = fmaxf(fmaf(-dm, dm, (hsum2(sq2[0]) + hsum2(sq2[1])) * inv), 0.f);
-              float sh, sh_unused;
-              unpack2(shift2, sh, sh_unused);
-              const float mean = dm - sh;
+              // E[x^2] - mean^2 in fp32: relative error of the variance ~ 1e-7 (1 + mean^2 / var), i.e. nothing
+              // until a row's mean is hundreds of its standard deviations
+              const float mean = (hsum2(sum2[0]) + hsum2(sum2[1])) * inv;
+              const float var = fmaxf(fmaf(-mean, mean, (hsum2(sq2[0]) + hsum2(sq2[1])) * inv), 0.f);
               const float rstd = 1.0f / sqrtf(var + g.ln_eps);
               g.ln_stats[(int64_t)((uint32_t)mt / (uint32_t)g.m_tiles_per_batch) * g.rows_per_batch + r] =
                   make_float2(rstd, -mean * rstd);
+            }
             }
           }
         }
@@ -1207,14 +1250,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
     if constexpr (TN == 192) {
       static_assert(TN != 192 || (ACT != ACT_SIGMOID && !PE && !QUANT), "192-column tiles: no pos-enc / quantised / sigmoid epilogue");
-      epilogue_loop192<ACT, RESID, EPI>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
+      epilogue_loop192<ACT, RESID, EPI>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES,
+                              reinterpret_cast<float2*>(smem + Cfg::ROWFAC_OFFSET) + (warp - 6) * 32, sstats, warp, lane,
                               (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, rank, BAR(PB_TFULL),
                               BAR(PB_TEMPTY));
     } else {
       static_assert(!(EPI & EPI_GATE), "the gate epilogue exists for 192-column tiles only");
       epilogue_loop<ACT, PE, RESID, QUANT, true, EPI>(g, smem + P_STAGES * P_STAGE_BYTES + (warp - 6) * EPI_STAGE_BYTES, warp, lane,
                                                  (uint32_t)first_tile, (uint32_t)tile_stride, (uint32_t)total_tiles, (uint32_t)UNITS, rank,
-                                                 BAR(PB_TFULL), BAR(PB_TEMPTY));
+                                                 BAR(PB_TFULL), BAR(PB_TEMPTY), sstats);
     }
   }
 
