@@ -14,12 +14,12 @@ M, K, N = [int(v) for v in sys.argv[1:4]] if len(sys.argv) > 3 else (48064, 192,
 x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / K ** 0.5
 ws = va.split_tf32(w)
 for _ in range(3): va.linear(x, w, None, tensor_cores=True, weight_split=ws)
-buf = torch.zeros(16 * 128 + 2 * 148, dtype=torch.int64, device="cuda")
+buf = torch.zeros(16 * 128 + 8 * 148, dtype=torch.int64, device="cuda")
 fn(ctypes.c_void_p(buf.data_ptr()))
 va.linear(x, w, None, tensor_cores=True, weight_split=ws)
 torch.cuda.synchronize()
 fn(None)
-cta = buf[16 * 128:].cpu().view(148, 2)
+cta = buf[16 * 128:].cpu().view(148, 8)[:, [0, 7]]
 t0 = int(cta[:, 0].min())
 dur = [(int(c[1]) - int(c[0])) / 1e3 for c in cta]
 start = [(int(c[0]) - t0) / 1e3 for c in cta]

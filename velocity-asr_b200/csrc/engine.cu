@@ -185,7 +185,7 @@ Dims make_dims(const vasr_handle* h, int64_t B, int64_t S, int64_t T) {
 }
 
 struct Work {
-  float *raw, *mean, *rstd, *melpad;
+  float *raw, *melpad;
   double* part;
   float* qscratch;      // probe output of a quantised projection during calibration (M x max N)
   float *xa, *xb, *u, *xz, *bcdt, *yg, *hbuf, *cat, *f3, *fm, *fused, *qb, *ob;
@@ -211,8 +211,6 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   if (need_mel) {
     t.part = a.take<double>(q.B * mel_fft_blocks(q.T) * q.n_mels * 2);
     t.raw = a.take<float>(q.B * q.T * q.n_mels);
-    t.mean = a.take<float>(q.B * q.n_mels);
-    t.rstd = a.take<float>(q.B * q.n_mels);
   }
   t.melpad = a.take<float>(q.B * q.Tp * q.n_mels);
   t.xa = a.take<float>(q.M * q.d);
@@ -743,11 +741,10 @@ int run_model(vasr_handle* h, const Dims& q, const Work& k, float* logits, float
   return VASR_OK;
 }
 
-// PCM (device) -> k.raw (+ mean/rstd when normalize)
+// PCM (device) -> k.raw (+ the partial statistics launch_mel_finish merges, when normalize)
 int run_mel(vasr_handle* h, const Dims& q, const Work& k, const float* pcm, int normalize, cudaStream_t s) {
   KL(launch_mel_fft(pcm, k.raw, normalize ? k.part : nullptr, q.B, q.S, q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w,
                     h->win, h->tw400, s, &h->launches, k.rag));
-  if (normalize) KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
   return VASR_OK;
 }
 
@@ -769,7 +766,6 @@ int run_mel_from_host(vasr_handle* h, const Dims& q, const Work& k, const float*
                       q.T, q.n_mels, h->fb_lo, h->fb_off, h->fb_w, h->win, h->tw400, s, &h->launches,
                       k.rag ? k.rag + b0 * RAG_STRIDE : nullptr));
   }
-  KL(launch_mel_stats_combine(k.part, k.mean, k.rstd, q.B, q.T, q.n_mels, s, &h->launches, k.rag));
   return VASR_OK;
 }
 
@@ -1106,8 +1102,8 @@ int vasr_log_mel(vasr_handle* h, const float* pcm_dev, int64_t B, int64_t S, int
   Work k;
   RET(ensure_workspace(h, q, true, false, &k));
   RET(run_mel(h, q, k, pcm_dev, normalize, s));
-  KL(launch_mel_finish(k.raw, normalize ? k.mean : nullptr, k.rstd, mel_dev, q.B, q.T, q.n_mels, q.T, 0, s,
-                       &h->launches));
+  KL(launch_mel_finish(k.raw, nullptr, nullptr, mel_dev, q.B, q.T, q.n_mels, q.T, 0, s, &h->launches, nullptr,
+                       normalize ? k.part : nullptr));
   return VASR_OK;
 }
 
@@ -1313,7 +1309,7 @@ static int transcribe_impl(vasr_handle* h, const float* pcm_dev, const float* pc
   timing_begin(h, s);
   if (host) RET(run_mel_from_host(h, q, k, pcm_host, s));
   else RET(run_mel(h, q, k, pcm_dev, 1, s));
-  KL(launch_mel_finish(k.raw, k.mean, k.rstd, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag));
+  KL(launch_mel_finish(k.raw, nullptr, nullptr, k.melpad, q.B, q.T, q.n_mels, q.Tp, 1, s, &h->launches, k.rag, k.part));
   RET(run_model(h, q, k, from_parts ? nullptr : k.logits, nullptr, nullptr, nullptr, s));
   if (from_parts) {
     KL(launch_ctc_collapse(k.pred, tokens_dev, lens_dev, q.B, q.L, 0, 1, s, &h->launches, k.rag, k.amax_val, k.amax_idx,

@@ -258,6 +258,16 @@ __device__ __forceinline__ void tile_coords(const TcArgs& g, int64_t tile64, int
 #endif
 constexpr int TRACE_SLOTS = 128;
 constexpr int TRACE_ROLES = 16;
+// pair kernel, per CTA: globaltimer at kernel entry, after griddepcontrol.wait, first accumulator complete, first
+// tile stored, last accumulator complete, exit (tools/gemm_timeline.py)
+constexpr int TRACE_CTA = 8;
+__device__ __forceinline__ void trace_cta(const TcArgs& g, int slot) {
+  if (g.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[TRACE_ROLES * TRACE_SLOTS + TRACE_CTA * blockIdx.x + slot] = (long long)t;
+  }
+}
 __device__ __forceinline__ void trace_ev(const TcArgs& g, int role, int idx) {
   if (g.trace && blockIdx.x == 0 && idx < TRACE_SLOTS) g.trace[role * TRACE_SLOTS + idx] = clock64();
 }
@@ -623,8 +633,24 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
           r4[i] = __ldg(reinterpret_cast<const float4*>(rrow + (int64_t)rr * g.ldr + 32 * j));
       }
     };
-    if (RESID) load_resid(0);
+    if (RESID) {
+      load_resid(0);
+      // the residual rows of the other two chunks are fetched after the accumulator has been handed back, with
+      // nothing left to hide a trip to HBM behind (tools/gemm_timeline.py: 6 us from "accumulator complete" to
+      // "tile stored", all of it exposed at the end of a launch): start them on their way to L2 now
+      if (cc == 0) {
+#pragma unroll
+        for (int j = 1; j < 3; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t rr = 4 * i + rsub;
+            if (col_ok[j] && mi0 + rr < rpb)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + (int64_t)rr * g.ldr + 32 * j));
+          }
+      }
+    }
     mbar_wait(bar_tfull0 + 8u * acc, (it >> 1) & 1u);
+    if (warp == 6 && lane == 0) { if (it == 0) trace_cta(g, 2); trace_cta(g, 4); }
     tc_fence_after();
     if (c_begin >= c_end) {
       tc_fence_before();
@@ -704,6 +730,7 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
       if (RESID) load_resid(2);
       emit(v0, 2);
     }
+    if (warp == 6 && lane == 0 && it == 0) trace_cta(g, 3);
   }
 }
 
@@ -1030,6 +1057,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWl)) : "memory");
   }
+  if (threadIdx.x == 0) trace_cta(g, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -1068,7 +1096,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t tmem_base = 0u;
   // barriers, tensor memory and the cluster handshake are set up; from here on global memory is touched, which
   // has to wait for the previous kernel (programmatic dependent launch, common.cuh)
+  if (threadIdx.x == 0) trace_cta(g, 6);
   pdl_wait();
+  if (threadIdx.x == 0) trace_cta(g, 1);
 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;   // pair tiles (256 rows)
@@ -1262,9 +1292,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if (threadIdx.x == 6 * 32) trace_cta(g, 5);        // epilogue warp 6 done
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();           // nobody leaves while the peer may still signal or read it
+  if (threadIdx.x == 0) trace_cta(g, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));

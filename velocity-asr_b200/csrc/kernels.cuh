@@ -105,19 +105,18 @@ enum { RAG_S = 0, RAG_T = 1, RAG_L = 2, RAG_K1 = 3, RAG_K2 = 4, RAG_STRIDE = 8 }
 // One pass PCM (B, S) -> raw (B, T, n_mels) = log(mel power + 1e-10): reflect padding by index, window,
 // 400-point FFT, power, band-sparse filterbank (weights fb_w[fb_off[j] .. fb_off[j+1]) on frequency bins
 // fb_lo[j] ...), log.  win: 400 taps; tw: 400 x (cos, -sin)(2 pi m / 400).  part (B, mel_fft_blocks(T),
-// n_mels, 2) doubles receives per-CTA (mean, M2) partials for launch_mel_stats_combine (NULL to skip).
+// n_mels, 2) doubles receives per-CTA (mean, M2) partials for launch_mel_finish (NULL to skip).
 int64_t mel_fft_blocks(int64_t T);
 cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B, int64_t S, int64_t T, int n_mels,
                            const int* fb_lo, const int* fb_off, const float* fb_w, const float* win,
                            const float* tw, cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr);
-// per (b, j): mean and 1/(unbiased std + 1e-10) over the T frames, from the partials above.
-cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
-                                     cudaStream_t s, int64_t* launches, const int32_t* rag = nullptr);
-// out[b, t + front, j] = (raw[b,t,j] - mean[b,j]) * rstd[b,j]  (mean == NULL: plain copy);
-// out has frames_per_utt rows per utterance; rows outside [front, front + T) are zeroed.
+// out[b, t + front, j] = (raw[b,t,j] - mean[b,j]) * rstd[b,j]; out has frames_per_utt rows per utterance, rows
+// outside [front, front + T) are zeroed.  The statistics — per (b, j) the mean and 1 / (unbiased std + 1e-10) over
+// the T frames — come from `part` (the partials of launch_mel_fft, merged inside the kernel) when given, else from
+// mean / rstd; with neither the kernel is a plain copy.
 cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* rstd, float* out, int64_t B,
                               int64_t T, int n_mels, int64_t frames_per_utt, int front, cudaStream_t s,
-                              int64_t* launches, const int32_t* rag = nullptr);
+                              int64_t* launches, const int32_t* rag = nullptr, const double* part = nullptr);
 
 // ---------------------------------------------------------------- global context --------
 // out[b, i, :] = mean_t x[b, floor(iL/K) .. ceil((i+1)L/K), :]   (attention.py:71-73)

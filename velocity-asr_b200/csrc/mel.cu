@@ -197,56 +197,63 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
   }
 }
 
-// One CTA per utterance, one thread per mel bin: Chan's pairwise update over the CTA partials in
-// frame order (deterministic), then mean and 1 / (unbiased std + 1e-10)  (audio.py:132-135).
-__global__ void __launch_bounds__(MAX_MELS) mel_stats_combine_kernel(const double* __restrict__ part,
-                                                                     float* __restrict__ mean,
-                                                                     float* __restrict__ rstd, int64_t T,
-                                                                     int nblk, int n_mels,
-                                                                     const int32_t* __restrict__ rag) {
-  pdl_trigger();
-  pdl_wait();
-  const int64_t b = blockIdx.x;
-  const int j = threadIdx.x;
-  if (j >= n_mels) return;
-  double n = 0.0, mu = 0.0, m2 = 0.0;
-  if (rag) T = rag[b * RAG_STRIDE + RAG_T];        // the partials keep the row stride nblk of the longest
-  const int nb = (int)((T + FPC - 1) / FPC);
-  for (int k = 0; k < nb; ++k) {
-    const double nk = (double)((T - (int64_t)k * FPC) < FPC ? (T - (int64_t)k * FPC) : FPC);
-    const double* p = part + ((b * nblk + k) * n_mels + j) * 2;
-    const double d = p[0] - mu;
-    const double nn = n + nk;
-    mu += d * (nk / nn);
-    m2 += p[1] + d * d * (n * nk / nn);
-    n = nn;
-  }
-  // torch.std(unbiased) of a single frame is NaN; keep that behaviour (0/0).
-  const double sd = sqrt(m2 / (double)(T - 1));
-  mean[b * n_mels + j] = (float)mu;
-  rstd[b * n_mels + j] = (float)(1.0 / (sd + 1e-10));
-}
-
+// Normalisation into the layout the temporal-binding projection reads.  With `part` the CTA first merges the
+// per-CTA (mean, M2) partials of mel_fft_kernel for its utterance — one thread per mel bin, Chan's pairwise update
+// in frame order, fp64: every CTA of an utterance computes the same bits — into mean and 1 / (unbiased std + 1e-10)
+// (audio.py:132-135); a separate one-CTA-per-utterance kernel for that cost a launch and 28 us on the critical path.
 __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict__ raw,
                                                          const float* __restrict__ mean,
-                                                         const float* __restrict__ rstd, float* __restrict__ out,
-                                                         int64_t T, int n_mels, int64_t fpu, int front,
-                                                         const int32_t* __restrict__ rag) {
+                                                         const float* __restrict__ rstd,
+                                                         const double* __restrict__ part, int nblk,
+                                                         float* __restrict__ out, int64_t T, int n_mels, int64_t fpu,
+                                                         int front, const int32_t* __restrict__ rag, int64_t per_cta) {
+  __shared__ float s_mean[MAX_MELS], s_rstd[MAX_MELS];
   pdl_trigger();
   pdl_wait();
   const int64_t b = blockIdx.y;
-  const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;
-  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= fpu * n_mels) return;
-  const int64_t p = idx / n_mels;
-  const int j = (int)(idx - p * n_mels);
-  const int64_t t = p - front;
-  float v = 0.f;
-  if (t >= 0 && t < Tb) {
-    v = raw[(b * T + t) * n_mels + j];
-    if (mean) v = (v - mean[b * n_mels + j]) * rstd[b * n_mels + j];
+  const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;   // the partials keep the row stride nblk of the longest
+  const bool norm = part != nullptr || mean != nullptr;
+  if (part) {
+    const int j = threadIdx.x;
+    if (j < n_mels) {
+      double n = 0.0, mu = 0.0, m2 = 0.0;
+      const int nb = (int)((Tb + FPC - 1) / FPC);
+      const double* p = part + (b * nblk * n_mels + j) * 2;
+      for (int k = 0; k < nb; ++k, p += 2 * n_mels) {
+        const double nk = (double)((Tb - (int64_t)k * FPC) < FPC ? (Tb - (int64_t)k * FPC) : FPC);
+        const double d = p[0] - mu;
+        const double nn = n + nk;
+        mu += d * (nk / nn);
+        m2 += p[1] + d * d * (n * nk / nn);
+        n = nn;
+      }
+      // torch.std(unbiased) of a single frame is NaN; keep that behaviour (0/0).
+      const double sd = sqrt(m2 / (double)(Tb - 1));
+      s_mean[j] = (float)mu;
+      s_rstd[j] = (float)(1.0 / (sd + 1e-10));
+    }
+    __syncthreads();
+  } else if (mean) {
+    if (threadIdx.x < n_mels) {
+      s_mean[threadIdx.x] = mean[b * n_mels + threadIdx.x];
+      s_rstd[threadIdx.x] = rstd[b * n_mels + threadIdx.x];
+    }
+    __syncthreads();
   }
-  out[b * fpu * n_mels + idx] = v;
+  const int64_t total = fpu * n_mels;
+  const int64_t i0 = (int64_t)blockIdx.x * per_cta;
+  const int64_t i1 = i0 + per_cta < total ? i0 + per_cta : total;
+  for (int64_t idx = i0 + threadIdx.x; idx < i1; idx += 256) {
+    const int64_t p = idx / n_mels;
+    const int j = (int)(idx - p * n_mels);
+    const int64_t t = p - front;
+    float v = 0.f;
+    if (t >= 0 && t < Tb) {
+      v = raw[(b * T + t) * n_mels + j];
+      if (norm) v = (v - s_mean[j]) * s_rstd[j];
+    }
+    out[b * total + idx] = v;
+  }
 }
 
 }  // namespace
@@ -268,24 +275,18 @@ cudaError_t launch_mel_fft(const float* pcm, float* raw, double* part, int64_t B
   return e;
 }
 
-cudaError_t launch_mel_stats_combine(const double* part, float* mean, float* rstd, int64_t B, int64_t T, int n_mels,
-                                     cudaStream_t s, int64_t* launches, const int32_t* rag) {
-  if (B <= 0) return cudaSuccess;
-  if (n_mels > MAX_MELS) return cudaErrorInvalidValue;
-  const cudaError_t e = launch_k(mel_stats_combine_kernel, dim3((unsigned)B), dim3(MAX_MELS), 0, s, part, mean, rstd, T,
-                                 (int)mel_fft_blocks(T), n_mels, rag);
-  if (launches) ++*launches;
-  return e;
-}
-
 cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* rstd, float* out, int64_t B,
                               int64_t T, int n_mels, int64_t frames_per_utt, int front, cudaStream_t s,
-                              int64_t* launches, const int32_t* rag) {
+                              int64_t* launches, const int32_t* rag, const double* part) {
   if (B <= 0) return cudaSuccess;
-  if (B > 65535) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)((frames_per_utt * n_mels + 255) / 256), (unsigned)B);
-  const cudaError_t e = launch_k(mel_finish_kernel, grid, dim3(256), 0, s, raw, mean, rstd, out, T, n_mels, frames_per_utt,
-                                 front, rag);
+  if (B > 65535 || n_mels > MAX_MELS) return cudaErrorInvalidValue;
+  // a CTA takes 16 K elements, or 1/32 of a long utterance (every CTA of an utterance repeats the merge of its partials)
+  const int64_t total = frames_per_utt * n_mels;
+  int64_t per_cta = total / 32 > 16384 ? total / 32 : 16384;
+  per_cta = (per_cta + 255) / 256 * 256;
+  dim3 grid((unsigned)((total + per_cta - 1) / per_cta), (unsigned)B);
+  const cudaError_t e = launch_k(mel_finish_kernel, grid, dim3(256), 0, s, raw, mean, rstd, part, (int)mel_fft_blocks(T), out,
+                                 T, n_mels, frames_per_utt, front, rag, per_cta);
   if (launches) ++*launches;
   return e;
 }
