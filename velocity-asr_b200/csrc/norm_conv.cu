@@ -60,12 +60,11 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
   }
 }
 
-// One warp = RUN consecutive tokens of one utterance.  The lane keeps its channels of the last
+// One warp = `run_len` consecutive tokens of one utterance (chosen by the launcher so that the grid is whole waves).  The lane keeps its channels of the last
 // k-1 normalised rows in registers (a sliding window), so every input row is read once, every
 // output row written once, and nothing goes through shared memory.  The k-1 rows before the run
 // are re-normalised by the warp (halo).  Rows are fetched two iterations ahead of their use so the
 // global-load latency overlaps the arithmetic of the rows in between.
-constexpr int RUN = 16;
 constexpr int MAXK = 8;
 constexpr int DW_PER = 6;   // channels per lane: C <= 192
 
@@ -74,12 +73,13 @@ __global__ void __launch_bounds__(128) ln_dwconv_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ w,
-                                                        const float* __restrict__ bias, int64_t L, int C) {
+                                                        const float* __restrict__ bias, int64_t L, int C,
+                                                        int run_len) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t run = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int64_t b = blockIdx.y;
-  const int64_t t0 = run * RUN;
+  const int64_t t0 = run * run_len;
   if (t0 >= L) return;
   float wv[DW_PER][K], bv[DW_PER], gv[DW_PER], be[DW_PER];
 #pragma unroll
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) ln_dwconv_kernel(const float* __restrict_
     for (int i = 0; i < DW_PER; ++i) win[j][i] = 0.f;
 
   const float invC = 1.0f / (float)C;
-  const int64_t tend = (t0 + RUN < L) ? t0 + RUN : L;
+  const int64_t tend = (t0 + run_len < L) ? t0 + run_len : L;
   const float* xb = x + b * L * C;
   auto fetch = [&](int64_t t, float (&dst)[DW_PER]) {
 #pragma unroll
@@ -171,11 +171,29 @@ cudaError_t launch_ln_dwconv(const float* x, float* u, const float* gamma, const
                              int64_t* launches) {
   if (B <= 0 || L <= 0) return cudaSuccess;
   if (C > 32 * DW_PER || k < 1 || k > MAXK || B > 65535) return cudaErrorInvalidValue;
-  const int64_t runs = (L + RUN - 1) / RUN;
+  // Run length: a warp re-normalises the k - 1 rows before its run, so its cost is run + k - 1 rows, and the grid
+  // runs in waves of (resident CTAs per SM) x SMs.  At config 2 runs of 16 tokens gave 768 CTAs for 592 resident
+  // ones — a second wave of 176 — where runs of 21 give one wave of 576 (24 rows per warp instead of 2 x 19).
+  static int slots = 0;
+  if (slots == 0) {
+    int dev = 0, sms = 148, occ = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_dwconv_kernel<4>, 128, 0) != cudaSuccess || occ < 1) occ = 4;
+    slots = occ * sms;
+  }
+  int run_len = 16;
+  int64_t best = -1;
+  for (int r = 4; r <= 64; ++r) {
+    const int64_t ctas = B * (((L + r - 1) / r + 3) / 4);
+    const int64_t cost = ((ctas + slots - 1) / slots) * (r + k - 1);
+    if (best < 0 || cost < best) { best = cost; run_len = r; }
+  }
+  const int64_t runs = (L + run_len - 1) / run_len;
   dim3 grid((unsigned)((runs + 3) / 4), (unsigned)B);
   cudaError_t e_launch = cudaSuccess;
   switch (k) {
-#define VASR_DW_CASE(KK) case KK: e_launch = launch_k(ln_dwconv_kernel<KK>, grid, dim3(128), 0, s, x, u, gamma, beta, w, bias, L, C); break;
+#define VASR_DW_CASE(KK) case KK: e_launch = launch_k(ln_dwconv_kernel<KK>, grid, dim3(128), 0, s, x, u, gamma, beta, w, bias, L, C, run_len); break;
     VASR_DW_CASE(1) VASR_DW_CASE(2) VASR_DW_CASE(3) VASR_DW_CASE(4)
     VASR_DW_CASE(5) VASR_DW_CASE(6) VASR_DW_CASE(7) VASR_DW_CASE(8)
 #undef VASR_DW_CASE
