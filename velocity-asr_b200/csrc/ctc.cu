@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(PARTS ? 256 : 32) ctc_collapse_kernel(int32_t*
     for (int64_t t = threadIdx.x; t < Lb; t += 256) {
       float best = -INFINITY;
       int bi = -1;
-      for (int s = 0; s < slots; ++s) {
+#pragma unroll 8
+      for (int s = 0; s < slots; ++s) {                // unrolled: the slots' loads are independent, the compares are not
         const int i = pi[(int64_t)s * M + b * L + t];
         const float v = pv[(int64_t)s * M + b * L + t];
         if (i >= 0 && (v > best || bi < 0)) { best = v; bi = i; }

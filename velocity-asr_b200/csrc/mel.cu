@@ -198,15 +198,17 @@ __global__ void __launch_bounds__(MEL_WARPS * 32) mel_fft_kernel(
 }
 
 // Normalisation into the layout the temporal-binding projection reads.  With `part` the CTA first merges the
-// per-CTA (mean, M2) partials of mel_fft_kernel for its utterance — one thread per mel bin, Chan's pairwise update
-// in frame order, fp64: every CTA of an utterance computes the same bits — into mean and 1 / (unbiased std + 1e-10)
-// (audio.py:132-135); a separate one-CTA-per-utterance kernel for that cost a launch and 28 us on the critical path.
+// per-CTA (mean, M2) partials of mel_fft_kernel for its utterance into mean and 1 / (unbiased std + 1e-10)
+// (audio.py:132-135), fp64, in a fixed order — every CTA of an utterance computes the same bits.  Two
+// division-free passes (grand mean, then sum of M2_k + n_k (mean_k - mean)^2): the first version
+// was a separate one-CTA-per-utterance kernel running Chan's update block by block, two fp64 divisions inside a
+// dependent chain of 47 steps — 28 us on the critical path for 5,120 numbers.
 __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict__ raw,
                                                          const float* __restrict__ mean,
                                                          const float* __restrict__ rstd,
                                                          const double* __restrict__ part, int nblk,
                                                          float* __restrict__ out, int64_t T, int n_mels, int64_t fpu,
-                                                         int front, const int32_t* __restrict__ rag, int64_t per_cta) {
+                                                         int front, const int32_t* __restrict__ rag, int per_cta) {
   __shared__ float s_mean[MAX_MELS], s_rstd[MAX_MELS];
   pdl_trigger();
   pdl_wait();
@@ -214,21 +216,43 @@ __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict
   const int64_t Tb = rag ? rag[b * RAG_STRIDE + RAG_T] : T;   // the partials keep the row stride nblk of the longest
   const bool norm = part != nullptr || mean != nullptr;
   if (part) {
-    const int j = threadIdx.x;
-    if (j < n_mels) {
-      double n = 0.0, mu = 0.0, m2 = 0.0;
-      const int nb = (int)((Tb + FPC - 1) / FPC);
-      const double* p = part + (b * nblk * n_mels + j) * 2;
-      for (int k = 0; k < nb; ++k, p += 2 * n_mels) {
-        const double nk = (double)((Tb - (int64_t)k * FPC) < FPC ? (Tb - (int64_t)k * FPC) : FPC);
-        const double d = p[0] - mu;
-        const double nn = n + nk;
-        mu += d * (nk / nn);
-        m2 += p[1] + d * d * (n * nk / nn);
-        n = nn;
+    // threads (j, g): mel bin j, every G-th block starting at g — the loads of a pass are in flight together, the
+    // G partial sums of a bin are added in the order of g (the same bits in every CTA of the utterance)
+    __shared__ double s_acc[256];
+    const int G = 256 / n_mels < 1 ? 1 : (256 / n_mels > 4 ? 4 : 256 / n_mels);
+    const int j = threadIdx.x % n_mels, g = threadIdx.x / n_mels;
+    const bool on = g < G;
+    const int nb = (int)((Tb + FPC - 1) / FPC);
+    const double last_n = (double)(Tb - (int64_t)(nb - 1) * FPC);
+    const double* p = part + (b * nblk * n_mels + j) * 2;
+    const int64_t st = 2 * n_mels;
+    double s = 0.0;
+    if (on) {
+#pragma unroll 8
+      for (int k = g; k < nb; k += G) s += (k == nb - 1 ? last_n : (double)FPC) * p[k * st];
+    }
+    s_acc[threadIdx.x] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int q = 0; q < G; ++q) tot += s_acc[q * n_mels + j];
+    const double mu = tot / (double)Tb;
+    __syncthreads();
+    double m2 = 0.0;
+    if (on) {
+#pragma unroll 8
+      for (int k = g; k < nb; k += G) {
+        const double2 pk = *reinterpret_cast<const double2*>(p + k * st);
+        const double d = pk.x - mu;
+        m2 += pk.y + (k == nb - 1 ? last_n : (double)FPC) * d * d;
       }
+    }
+    s_acc[threadIdx.x] = m2;
+    __syncthreads();
+    if (g == 0) {
+      double m2t = 0.0;
+      for (int q = 0; q < G; ++q) m2t += s_acc[q * n_mels + j];
       // torch.std(unbiased) of a single frame is NaN; keep that behaviour (0/0).
-      const double sd = sqrt(m2 / (double)(Tb - 1));
+      const double sd = sqrt(m2t / (double)(Tb - 1));
       s_mean[j] = (float)mu;
       s_rstd[j] = (float)(1.0 / (sd + 1e-10));
     }
@@ -240,19 +264,42 @@ __global__ void __launch_bounds__(256) mel_finish_kernel(const float* __restrict
     }
     __syncthreads();
   }
-  const int64_t total = fpu * n_mels;
-  const int64_t i0 = (int64_t)blockIdx.x * per_cta;
-  const int64_t i1 = i0 + per_cta < total ? i0 + per_cta : total;
-  for (int64_t idx = i0 + threadIdx.x; idx < i1; idx += 256) {
-    const int64_t p = idx / n_mels;
-    const int j = (int)(idx - p * n_mels);
-    const int64_t t = p - front;
+  const uint32_t total = (uint32_t)(fpu * n_mels);            // checked by the launcher to fit
+  const uint32_t i0 = blockIdx.x * (uint32_t)per_cta;
+  const uint32_t i1 = i0 + (uint32_t)per_cta < total ? i0 + (uint32_t)per_cta : total;
+  const float* rb = raw + b * T * n_mels;
+  float* ob = out + b * (int64_t)total;
+  if ((n_mels & 3) == 0 && (reinterpret_cast<uintptr_t>(rb) & 15) == 0 && (reinterpret_cast<uintptr_t>(ob) & 15) == 0) {
+    // four mel bins of one frame per thread and access (a group never straddles a frame: n_mels % 4 == 0)
+#pragma unroll 4
+    for (uint32_t idx = i0 + 4 * threadIdx.x; idx < i1; idx += 1024) {
+      const uint32_t p = idx / (uint32_t)n_mels;
+      const uint32_t j = idx - p * (uint32_t)n_mels;
+      const int64_t t = (int64_t)p - front;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= 0 && t < Tb) {
+        v = __ldg(reinterpret_cast<const float4*>(rb + t * n_mels + j));
+        if (norm) {
+          v.x = (v.x - s_mean[j]) * s_rstd[j];
+          v.y = (v.y - s_mean[j + 1]) * s_rstd[j + 1];
+          v.z = (v.z - s_mean[j + 2]) * s_rstd[j + 2];
+          v.w = (v.w - s_mean[j + 3]) * s_rstd[j + 3];
+        }
+      }
+      *reinterpret_cast<float4*>(ob + idx) = v;
+    }
+    return;
+  }
+  for (uint32_t idx = i0 + threadIdx.x; idx < i1; idx += 256) {
+    const uint32_t p = idx / (uint32_t)n_mels;
+    const uint32_t j = idx - p * (uint32_t)n_mels;
+    const int64_t t = (int64_t)p - front;
     float v = 0.f;
     if (t >= 0 && t < Tb) {
-      v = raw[(b * T + t) * n_mels + j];
+      v = rb[t * n_mels + j];
       if (norm) v = (v - s_mean[j]) * s_rstd[j];
     }
-    out[b * total + idx] = v;
+    ob[idx] = v;
   }
 }
 
@@ -280,13 +327,14 @@ cudaError_t launch_mel_finish(const float* raw, const float* mean, const float* 
                               int64_t* launches, const int32_t* rag, const double* part) {
   if (B <= 0) return cudaSuccess;
   if (B > 65535 || n_mels > MAX_MELS) return cudaErrorInvalidValue;
-  // a CTA takes 16 K elements, or 1/32 of a long utterance (every CTA of an utterance repeats the merge of its partials)
+  // a CTA takes 8 K elements, or 1/128 of a long utterance (every CTA of an utterance repeats the merge of its partials)
   const int64_t total = frames_per_utt * n_mels;
-  int64_t per_cta = total / 32 > 16384 ? total / 32 : 16384;
-  per_cta = (per_cta + 255) / 256 * 256;
+  if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+  int64_t per_cta = total / 128 > 8192 ? total / 128 : 8192;
+  per_cta = (per_cta + 1023) / 1024 * 1024;
   dim3 grid((unsigned)((total + per_cta - 1) / per_cta), (unsigned)B);
   const cudaError_t e = launch_k(mel_finish_kernel, grid, dim3(256), 0, s, raw, mean, rstd, part, (int)mel_fft_blocks(T), out,
-                                 T, n_mels, frames_per_utt, front, rag, per_cta);
+                                 T, n_mels, frames_per_utt, front, rag, (int)per_cta);
   if (launches) ++*launches;
   return e;
 }

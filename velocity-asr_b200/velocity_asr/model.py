@@ -272,18 +272,21 @@ class VELOCITYASR(nn.Module):
         back and turned into lists.  Yields one List[List[int]] per input batch, in order; results
         are identical to calling transcribe() on each batch.  Batches are (B, S) float32 CPU
         tensors (pin them for full PCIe speed); shapes may change from batch to batch.  An item may also
-        be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths).
+        be a pair (batch, lengths): a ragged batch, as transcribe(batch, lengths=lengths).  The input iterator is
+        read one batch ahead of the batch being computed.
         as_arrays=True yields (tokens (B, L) int32 left-packed, counts (B,) int32) numpy copies instead of lists:
         the compact form sharding.gather_token_arrays exchanges between ranks."""
         dev = self._exec_device()
         eng = self._engine(dev)
         comp = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
-        slots = [dict(pcm=None, tok=None, lens=None, tok_h=None, lens_h=None,
-                      h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
-        pending = None          # (slot, B) of the batch whose results are still on the device
-        i = 0
-        for audio in batches:
+        # three device slots: the batch whose kernels run, the next one (its host->device copy is issued as soon as
+        # the current batch's kernels are queued, i.e. a whole step ahead of its use: with 8 ranks sharing the host's
+        # PCIe and memory a 61 MB copy takes several ms) and the previous one (results not yet collected)
+        slots = [dict(pcm=None, tok=None, lens=None, tok_h=None, lens_h=None, shape=None, slen=None,
+                      h2d=torch.cuda.Event(), done=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(3)]
+
+        def stage(audio, sl):
             slen = None
             if isinstance(audio, (tuple, list)):        # (padded batch, per-utterance sample counts): ragged
                 audio, slen = audio
@@ -294,7 +297,6 @@ class VELOCITYASR(nn.Module):
             audio = audio.to(torch.float32).contiguous()
             B, S = audio.shape
             L = self.get_output_length(1 + S // 160)
-            sl = slots[i % 2]
             if sl["pcm"] is None or sl["pcm"].shape != (B, S):
                 sl["pcm"] = torch.empty(B, S, device=dev, dtype=torch.float32)
                 sl["tok"] = torch.empty(B, L, device=dev, dtype=torch.int32)
@@ -306,12 +308,24 @@ class VELOCITYASR(nn.Module):
                 copy.wait_event(sl["free"])      # the kernels that last read this slot's PCM are done
                 sl["pcm"].copy_(audio, non_blocking=True)
                 sl["h2d"].record(copy)
+            sl["shape"], sl["slen"] = (B, S), slen
+            sl["src"] = audio                    # keeps a converted copy alive until the transfer has been consumed
+            return sl
+
+        it = iter(batches)
+        first = next(it, None)
+        staged = stage(first, slots[0]) if first is not None else None
+        pending = None          # slot of the batch whose results are still on the device
+        i = 0
+        while staged is not None:
+            sl = staged
+            B, S = sl["shape"]
             comp.wait_event(sl["h2d"])
-            if slen is None:
+            if sl["slen"] is None:
                 _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(sl["pcm"]), B, S, _native.ptr(sl["tok"]),
                                                       _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
             else:
-                slen_t = _lengths_tensor(slen, B)       # stays referenced across the call (read synchronously)
+                slen_t = _lengths_tensor(sl["slen"], B)  # stays referenced across the call (read synchronously)
                 _native.check(eng.lib.vasr_transcribe_ragged(
                     eng.handle, _native.ptr(sl["pcm"]), _native.ptr(slen_t), B, S,
                     _native.ptr(sl["tok"]), _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
@@ -319,10 +333,12 @@ class VELOCITYASR(nn.Module):
             sl["tok_h"].copy_(sl["tok"], non_blocking=True)
             sl["lens_h"].copy_(sl["lens"], non_blocking=True)
             sl["done"].record(comp)
+            i += 1
+            nxt = next(it, None)
+            staged = stage(nxt, slots[i % 3]) if nxt is not None else None
             if pending is not None:
                 yield self._collect(pending, as_arrays)
             pending = sl
-            i += 1
         if pending is not None:
             yield self._collect(pending, as_arrays)
 
