@@ -241,8 +241,15 @@ class VELOCITYASR(nn.Module):
         slen = None if lengths is None else _lengths_tensor(lengths, B)
         if audio.device.type == "cpu":
             pcm = audio.to(torch.float32).contiguous()
-            tokens = torch.empty(B, L, dtype=torch.int32, pin_memory=True)
-            lens = torch.empty(B, dtype=torch.int32, pin_memory=True)
+            # pinned result buffers are kept per shape: a cudaHostAlloc per call costs more than the D2H itself
+            # (the lists returned below are copies)
+            cache = self.__dict__.setdefault("_pinned_out", {})
+            if (B, L) not in cache:
+                if len(cache) >= 8:
+                    cache.clear()
+                cache[(B, L)] = (torch.empty(B, L, dtype=torch.int32, pin_memory=True),
+                                 torch.empty(B, dtype=torch.int32, pin_memory=True))
+            tokens, lens = cache[(B, L)]
             if slen is None:
                 _native.check(eng.lib.vasr_transcribe_host(eng.handle, _native.ptr(pcm), B, S, _native.ptr(tokens),
                                                            _native.ptr(lens)))
@@ -280,6 +287,7 @@ class VELOCITYASR(nn.Module):
         eng = self._engine(dev)
         comp = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
+        back = torch.cuda.Stream(dev)
         # three device slots: the batch whose kernels run, the next one (its host->device copy is issued as soon as
         # the current batch's kernels are queued, i.e. a whole step ahead of its use: with 8 ranks sharing the host's
         # PCIe and memory a 61 MB copy takes several ms) and the previous one (results not yet collected)
@@ -321,6 +329,7 @@ class VELOCITYASR(nn.Module):
             sl = staged
             B, S = sl["shape"]
             comp.wait_event(sl["h2d"])
+            comp.wait_event(sl["done"])          # the slot's previous results have left the device buffers
             if sl["slen"] is None:
                 _native.check(eng.lib.vasr_transcribe(eng.handle, _native.ptr(sl["pcm"]), B, S, _native.ptr(sl["tok"]),
                                                       _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
@@ -330,9 +339,13 @@ class VELOCITYASR(nn.Module):
                     eng.handle, _native.ptr(sl["pcm"]), _native.ptr(slen_t), B, S,
                     _native.ptr(sl["tok"]), _native.ptr(sl["lens"]), ctypes.c_void_p(comp.cuda_stream)))
             sl["free"].record(comp)
-            sl["tok_h"].copy_(sl["tok"], non_blocking=True)
-            sl["lens_h"].copy_(sl["lens"], non_blocking=True)
-            sl["done"].record(comp)
+            # results travel on a stream of their own: on the compute stream the two small D2H copies would sit
+            # between this batch's last kernel and the next batch's first
+            with torch.cuda.stream(back):
+                back.wait_event(sl["free"])
+                sl["tok_h"].copy_(sl["tok"], non_blocking=True)
+                sl["lens_h"].copy_(sl["lens"], non_blocking=True)
+                sl["done"].record(back)
             i += 1
             nxt = next(it, None)
             staged = stage(nxt, slots[i % 3]) if nxt is not None else None
