@@ -802,6 +802,44 @@ def test_non_default_local_stack_config(va):
         va.VELOCITYASR(va.VelocityASRConfig(attention_heads=8, attention_dim=64)).cuda()(mel)   # > 4 heads
 
 
+@pytest.mark.parametrize("d_model", [96, 128, 160])
+def test_other_model_widths(va, d_model):
+    """Widths at which the fused epilogues do or do not apply (csrc/engine.cu can_fold_ln, gate_perm_row): 160 folds the
+    LayerNorms (five k-blocks) but keeps gate_mix (160 % 64 != 0); 128 keeps the LayerNorm launches, logits and
+    argmax_kernel (four k-blocks = the A slots) but mixes the gate in the epilogue; 96 keeps both.  Against the oracle;
+    the fused decode must agree with greedy decode of the logits."""
+    torch.manual_seed(5)
+    cfg = dict(d_model=d_model, ssm_layers=2, global_ssm_layers=1)
+    m = va.VELOCITYASR(va.VelocityASRConfig(scan_mode="sequential", **cfg))
+    m.load_state_dict(FU.amplify_state_dict(m.state_dict(), seed=6))
+    m = m.cuda().eval()
+    audio = FU.synth_audio(3, 20000, seed=9)
+    mel = va.compute_mel_spectrogram(audio.cuda())
+    got = m(mel)
+    want = O.forward(mel.double().cpu().numpy(), np_sd(m), dict(scan_mode="sequential", **cfg))
+    assert rel(got, want) < LOGIT_RTOL
+    assert m.transcribe(audio.cuda()) == va.ctc_greedy_decode(got)
+    assert m.transcribe(audio) == va.ctc_greedy_decode(got)            # host entry point
+
+
+def test_fused_argmax_ties_go_to_the_lowest_index(va):
+    """Greedy decode takes the head's per-slot argmax partials (GemmArgs::amax_val): with a zero head weight every
+    frame's logits are the bias, so exact ties are under control — inside one 32-column chunk, across the two halves
+    of an n-tile and across n-tiles the first maximum must win, as torch.argmax (decode.py:46)."""
+    m = make_model(va, "sequential")
+    audio = FU.synth_audio(2, 16000, seed=2)
+    for hot, want in (((5, 6), 5), ((40, 100), 40), ((130, 700), 130), ((999, 3), 3), ((64, 63), 63)):
+        with torch.no_grad():
+            m.ctc_head.proj["2"].weight.zero_()
+            b = torch.full((1000,), -1.0)
+            b[list(hot)] = 2.5
+            m.ctc_head.proj["2"].bias.copy_(b)
+        m.refresh_weights()
+        logits = m(va.compute_mel_spectrogram(audio.cuda()))
+        assert int(logits[0, 0].argmax()) == want and float(logits[0, 0].max()) == 2.5
+        assert m.transcribe(audio.cuda()) == [[want], [want]]
+
+
 def test_calls_on_one_handle_are_ordered_across_streams(va):
     """An asynchronous forward on the caller's stream followed at once by a host-tensor transcribe (which runs on the
     handle's own stream) share the workspace: the second call must wait for the first on the device."""

@@ -353,6 +353,9 @@ void fold_ln(const std::vector<float>& W, int64_t N, int64_t K, const float* bia
     (*sf)[(size_t)n] = (float)ss;
   }
 }
+// The folded form needs K = d in whole 32-deep k-blocks and more k-blocks than A slots (kernels.cuh, GemmArgs::ln_s);
+// other widths keep the LayerNorm launch in front of the plain projection.
+bool can_fold_ln(int d) { return d % 32 == 0 && d / 32 > 4; }
 int upload_folded(vasr_handle* h, const std::vector<float>& W, int64_t N, int64_t K, const float* bias,
                   const std::string& gk, const std::string& bk, float** Wd, float** bd, float** sd) {
   const std::vector<float>*g, *b;
@@ -409,7 +412,14 @@ int pack_block(vasr_handle* h, const std::string& p, int N, int expand, int ks, 
   const std::vector<float>*f1w, *f1b;
   RET(need(h, p + "ffn.0.weight", (int64_t)di * d, &f1w));
   RET(need(h, p + "ffn.0.bias", di, &f1b));
-  RET(upload_folded(h, *f1w, di, d, f1b->data(), p + "norm2.weight", p + "norm2.bias", &w->w_f1, &w->b_f1, &w->s_f1));
+  w->s_f1 = nullptr;
+  // ffn.0's folded variant exists for the 192-column tiling only: di = 192 a + (0 or >= 128) columns
+  if (can_fold_ln(d) && (di % 192 == 0 || di % 192 >= 128)) {
+    RET(upload_folded(h, *f1w, di, d, f1b->data(), p + "norm2.weight", p + "norm2.bias", &w->w_f1, &w->b_f1, &w->s_f1));
+  } else {
+    RET(upload(h, f1w->data(), f1w->size(), &w->w_f1));
+    RET(upload(h, f1b->data(), f1b->size(), &w->b_f1));
+  }
   RET(up(h, p + "ffn.3.weight", (int64_t)d * di, &w->w_f2));
   RET(up(h, p + "ffn.3.bias", d, &w->b_f2));
   return VASR_OK;
@@ -652,7 +662,12 @@ int run_block(vasr_handle* h, const BlockW& w, const Work& k, float* x, float* x
              nullptr, 0, s));
   RET(run_scan(h, w, k, B, L, quirk, s));
   RET(linear(h, k.yg, di, w.w_out, nullptr, x1, d, M, di, d, ACT_NONE, 0, x, d, s));
-  RET(linear_ln(h, k, x1, d, w.w_f1, w.b_f1, w.s_f1, k.hbuf, di, M, d, di, ACT_GELU, s));    // norm2 folded into ffn.0
+  if (w.s_f1) {
+    RET(linear_ln(h, k, x1, d, w.w_f1, w.b_f1, w.s_f1, k.hbuf, di, M, d, di, ACT_GELU, s));    // norm2 folded into ffn.0
+  } else {
+    KL(launch_layer_norm(x1, d, k.u, d, w.ln2_g, w.ln2_b, M, d, s, &h->launches));
+    RET(linear(h, k.u, d, w.w_f1, w.b_f1, k.hbuf, di, M, d, di, ACT_GELU, 0, nullptr, 0, s));
+  }
   RET(linear(h, k.hbuf, di, w.w_f2, w.b_f2, x, d, M, di, d, ACT_NONE, 0, x1, d, s));
   return VASR_OK;
 }
@@ -1028,7 +1043,7 @@ int vasr_commit_weights(vasr_handle* h) {
   bkv.insert(bkv.end(), vb->begin(), vb->end());
   RET(upload(h, wkv.data(), wkv.size(), &h->w_kv));
   RET(upload(h, bkv.data(), bkv.size(), &h->b_kv));
-  if (!h->quant) {
+  if (!h->quant && can_fold_ln(d)) {
     const std::vector<float>*qw, *qb;
     RET(need(h, gc + "cross_attention.q_proj.weight", (int64_t)att * d, &qw));
     RET(need(h, gc + "cross_attention.q_proj.bias", att, &qb));
@@ -1077,7 +1092,7 @@ int vasr_commit_weights(vasr_handle* h) {
   RET(up(h, "ctc_head.proj.0.bias", d, &h->ctc_b));
   RET(up_w(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, c.vocab_size, &h->w_ctc));
   RET(up(h, "ctc_head.proj.2.bias", c.vocab_size, &h->b_ctc));
-  if (!h->quant) {
+  if (!h->quant && can_fold_ln(d)) {
     const std::vector<float>*hw, *hb;
     RET(need(h, "ctc_head.proj.2.weight", (int64_t)c.vocab_size * d, &hw));
     RET(need(h, "ctc_head.proj.2.bias", c.vocab_size, &hb));
