@@ -221,7 +221,7 @@ size_t carve(vasr_handle* h, const Dims& q, bool need_mel, bool need_logits, Wor
   t.yg = a.take<float>(q.M * q.di);
   t.hbuf = a.take<float>(q.M * q.di);
   t.cat = a.take<float>(q.M * 2 * q.d);
-  t.f3 = a.take<float>(q.M * 3 * q.d);
+  if (!h->w_f3p) t.f3 = a.take<float>(q.M * 3 * q.d);      // gate | local | global before gate_mix: only without the gate epilogue
   t.fm = a.take<float>(q.M * q.d);
   t.fused = a.take<float>(q.M * q.d);
   t.qb = a.take<float>(q.M * q.att);
