@@ -1,4 +1,4 @@
-"""Pipeline trace of the tensor-core projection kernel (VASR_GEMM=tc1: single-CTA version): clock64 stamps of CTA 0 at
+"""Pipeline trace of the tensor-core projection kernel: clock64 stamps of CTA 0 at
 TMA issue (P), converter sees the tile (C0), converter done (C1), MMA warp released (M0), MMAs issued (M1)."""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -778,11 +778,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = (int)((g.K + TBK - 1) / TBK);
   const int64_t total_tiles = (int64_t)g.n_tiles * g.m_tiles_per_batch * g.n_batches;
   const int64_t UNITS = gridDim.x;
-  if (g.trace && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g.trace[TRACE_ROLES * TRACE_SLOTS + 2 * blockIdx.x] = (long long)t;
-  }
+  if (threadIdx.x == 0) trace_cta(g, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -908,11 +904,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (g.trace && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g.trace[TRACE_ROLES * TRACE_SLOTS + 2 * blockIdx.x + 1] = (long long)t;
-  }
+  if (threadIdx.x == 0) trace_cta(g, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
