@@ -822,6 +822,22 @@ def test_other_model_widths(va, d_model):
     assert m.transcribe(audio) == va.ctc_greedy_decode(got)            # host entry point
 
 
+def test_folded_layernorm_survives_a_common_offset(va):
+    """LayerNorm folded into the projection (csrc/gemm_tc.cu, EPI_LNA): the row statistics are sums of the row SHIFTED
+    by the mean of its first 32 channels, and the shifted row is what the tensor core multiplies — so a common offset
+    of the rows (which LayerNorm removes) costs no digits.  Without the shift an offset of 30 standard deviations
+    left 2e-4 of the largest logit (E[x^2] - mean^2 cancels as (mean / std)^2)."""
+    m = make_model(va, "sequential", amp=True)
+    sd = np_sd(m)
+    x0 = np.random.RandomState(3).standard_normal((2, 75, 192)).astype(np.float32)
+    for c in (0.0, 30.0, 300.0):
+        x = (x0 + np.float32(c)).astype(np.float32)
+        xt = torch.from_numpy(x).cuda()
+        assert rel(m.run_ctc_head(xt), O.ctc_head(x.astype(np.float64), sd)) < 1e-5
+        assert rel(m.run_ssm_block(xt, 3, "local"),
+                   O.ssm_block(x.astype(np.float64), sd, "local_ssm.layers.3.", "sequential")) < 2e-5
+
+
 def test_fused_argmax_ties_go_to_the_lowest_index(va):
     """Greedy decode takes the head's per-slot argmax partials (GemmArgs::amax_val): with a zero head weight every
     frame's logits are the bias, so exact ties are under control — inside one 32-column chunk, across the two halves
