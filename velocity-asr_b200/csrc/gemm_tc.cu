@@ -436,7 +436,7 @@ __device__ __forceinline__ void epilogue_loop(const TcArgs& g, uint8_t* stg, int
       }
       tmem_ld_wait();
       if constexpr ((EPI & EPI_LNA) != 0) {
-        // thread = row:  rstd * acc + (-mean * rstd * s[n] + bias[n])  on the chunks as they sit in registers
+        // thread = row:  rstd * acc + (-(mean - c) * rstd * s[n] + bias[n])  on the chunks as they sit in registers
         const u64 rs2 = pack2(own.x, own.x), ms2 = pack2(own.y, own.y);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -662,7 +662,7 @@ __device__ __forceinline__ void epilogue_loop192(const TcArgs& g, uint8_t* stg, 
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c_begin * 32;
     tmem_ld32_issue(taddr, v0);
     if (c_begin + 1 < c_end) tmem_ld32_issue(taddr + 32, v1);
-    // EPI_LNA: the thread that owns a row of the accumulator fetches the row's (rstd, -mean * rstd) and leaves
+    // EPI_LNA: the thread that owns a row of the accumulator fetches the row's (rstd, -(mean - c) * rstd) and leaves
     // them in this warp's row-factor table; after the transpose a lane picks up the factors of each of its rows
     // next to the row segment itself (no long-lived registers, no per-column loads: the GELU epilogue is the
     // critical path of ffn.0, every instruction here is paid in full)
