@@ -443,8 +443,15 @@ def run_own_arm(args):
     #     (velocity_asr.sharding.gather_token_arrays: fixed-size int32 arrays over a gloo group, no pickling) inside
     #     the timed region: the design's only exchange; every rank still builds the token lists of its own shard.
     #     (b) one blocking transcribe(host batch) call per step.
-    for _ in model.transcribe_batches(host[i % n_sets] for i in range(max(2, args.warmup))):
-        pass
+    if world == 1:
+        for _ in model.transcribe_batches(host[i % n_sets] for i in range(max(2, args.warmup))):
+            pass
+    else:
+        # warm-up includes the gather: the first collective on a gloo group sets up its TCP pairs (milliseconds,
+        # growing with the number of ranks), which is connection set-up, not a step
+        for tok_np, len_np in model.transcribe_batches((host[i % n_sets] for i in range(max(2, args.warmup))),
+                                                       as_arrays=True):
+            gather_token_arrays(tok_np, len_np, group=host_group, dst=0)
     barrier()
     t0 = time.perf_counter()
     n_out = n_all = 0
