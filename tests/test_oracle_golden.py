@@ -239,3 +239,57 @@ def test_quantized_modules_one_by_one(golden):
         d = np.abs(out - want)
         assert d.max() <= 1.001 * scale + 1e-6, (n, d.max(), scale)
         assert (d < 1e-3 * scale).mean() > 0.995, n
+
+
+# ------------------------------------------------------------------ host-side algebra of the fused epilogues -----
+def test_layernorm_fold_identity():
+    """The algebra csrc/engine.cu fold_ln and the EPI_LNA epilogue of csrc/gemm_tc.cu rely on (ssm.py:423-425,
+    model.py:229-239, attention.py:306-307):  Linear(LayerNorm(x)) = rstd ((x - c) W'^T) - (mean - c) rstd s + b'
+    with W' = W diag(gamma), b' = b + W beta, s[n] = sum_k W'[n, k], for any shift c (the kernel takes the mean of
+    the row's first 32 channels).  In fp64 it is exact; in fp32 the shifted form keeps its digits under a common
+    offset of the rows where E[x^2] - mean^2 of the raw row does not."""
+    rs = np.random.RandomState(11)
+    K, N = 192, 40
+    W, b = rs.standard_normal((N, K)) / K ** 0.5, rs.standard_normal(N)
+    gamma, beta = 1 + 0.3 * rs.standard_normal(K), 0.2 * rs.standard_normal(K)
+    Wf, bf, s = W * gamma, b + W @ beta, (W * gamma).sum(1)
+    for offset in (0.0, 30.0, 300.0):
+        x = rs.standard_normal((7, K)) + offset
+        want = O.linear(O.layer_norm(x, gamma, beta), W, b)
+        c = x[:, :32].mean(1, keepdims=True)
+        xs = x - c
+        dm = xs.mean(1, keepdims=True)
+        rstd = 1.0 / np.sqrt((xs * xs).mean(1, keepdims=True) - dm * dm + 1e-5)
+        got = rstd * (xs @ Wf.T) - dm * rstd * s + bf
+        assert np.abs(got - want).max() < 1e-9 * (1 + offset)
+        # fp32 statistics: raw sums lose (mean / std)^2 digits, shifted sums do not
+        x32 = x.astype(np.float32)
+        m_raw = x32.mean(1, dtype=np.float32)
+        var_raw = (x32 * x32).mean(1, dtype=np.float32) - m_raw * m_raw
+        xs32 = x32 - x32[:, :32].mean(1, keepdims=True, dtype=np.float32)
+        dm32 = xs32.mean(1, dtype=np.float32)
+        var_sh = (xs32 * xs32).mean(1, dtype=np.float32) - dm32 * dm32
+        var64 = x32.astype(np.float64).var(1)                     # of the values the kernel sees
+        assert np.abs(var_sh / var64 - 1).max() < 2e-6
+        if offset >= 300.0:
+            assert np.abs(var_raw / var64 - 1).max() > 1e-4
+
+
+def test_gate_rows_permutation():
+    """csrc/engine.cu gate_perm_row: rows of the stacked gate | local | global projection (attention.py:191-220)
+    re-ordered so that each 96-column half of a 192-column tile holds the three 32-row chunks of the SAME 32
+    channels — what one epilogue warp of the EPI_GATE variant needs to mix them in registers."""
+    C = 192
+
+    def gate_perm_row(rp):
+        t, a, j, i = rp // 192, (rp % 192) // 96, (rp % 96) // 32, rp % 32
+        return j * C + 64 * t + 32 * a + i
+
+    src = [gate_perm_row(rp) for rp in range(3 * C)]
+    assert sorted(src) == list(range(3 * C))
+    for rp in range(0, 3 * C, 96):
+        chans = [[r % C for r in src[rp + 32 * j: rp + 32 * j + 32]] for j in range(3)]
+        assert chans[0] == chans[1] == chans[2] == list(range(chans[0][0], chans[0][0] + 32))
+        assert [src[rp + 32 * j] // C for j in range(3)] == [0, 1, 2]
+        # output columns of the half: 64 * tile + 32 * half
+        assert chans[0][0] == 64 * (rp // 192) + 32 * ((rp % 192) // 96)
